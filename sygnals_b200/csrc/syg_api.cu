@@ -1,0 +1,971 @@
+// sygnals_b200/csrc/syg_api.cu -- the C ABI of libsygb200.so (include/sygb200.h): argument validation, plan
+// (constant table) cache, workspace management, chunking and kernel dispatch.  No CPU compute path exists here:
+// every entry point either launches the sm_100a kernels of syg_kernels.cuh or fails with an error code.
+//
+// Reference functions replaced (paths relative to the reference tree):
+//   syg_features_*   sygnals/core/features/manager.py:78-445 extract_features() and the per-feature functions
+//   syg_stft_*       sygnals/core/dsp.py:167-229 compute_stft()
+//   syg_psd_welch_*  sygnals/core/dsp.py:495-560 compute_psd_welch(), :434-493 compute_psd_periodogram()
+//   syg_segment_*    sygnals/core/segmentation.py:25-117 segment_fixed_length()
+#include "../../include/sygb200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "syg_kernels.cuh"
+#include "syg_plan.h"
+
+#ifndef SYG_EMU
+#define SYG_OCCUPANCY(nb, kernel, threads, smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(nb), kernel, threads, smem)
+#else
+#define SYG_OCCUPANCY(nb, kernel, threads, smem) ((nb) = 2, cudaSuccess)
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? SYG_E_NOMEM : SYG_E_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(e_));                                                   \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SYG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = (bytes + 255) / 256 * 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(SYG_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return SYG_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Lane {                      // one in-flight chunk of a *_host_* call
+    cudaStream_t stream = nullptr;
+    DevBuf in, out0, out1, starts, valid, ws;
+};
+
+}  // namespace
+
+struct syg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t ws_limit = (size_t)64 << 20;
+    std::mutex mu;
+    std::map<std::string, void*> tables;
+    std::map<std::string, std::vector<int>> host_ints;
+    DevBuf ws;                      // workspace of the device-pointer entry points
+    Lane lanes[2];
+    // optional per-kernel timing (syg_ctx_profile_*): event pairs around every launch, summed on read
+    bool prof_on = false;
+    struct ProfPair { cudaEvent_t a, b; int kind; };
+    std::vector<ProfPair> prof_pairs;
+    double prof_ms[3] = {0, 0, 0};
+    long long prof_n[3] = {0, 0, 0};
+};
+
+namespace {
+enum { PROF_FRAME = 0, PROF_FINALIZE = 1, PROF_WELCH = 2 };
+struct ProfScope {
+    syg_ctx* c; cudaStream_t st; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(syg_ctx* c_, cudaStream_t st_, int kind_) : c(c_), st(st_), kind(kind_) {
+        if (c->prof_on && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+        else a = b = nullptr;
+    }
+    ~ProfScope() {
+        if (a && b) { cudaEventRecord(b, st); c->prof_pairs.push_back({a, b, kind}); }
+    }
+};
+}  // namespace
+
+namespace {
+
+bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2i(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
+
+// ---------------------------------------------------------------------------------------------- plan tables
+template <class T>
+int upload_table(syg_ctx* ctx, const std::string& key, const std::vector<T>& host, const T** out) {
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) { *out = reinterpret_cast<const T*>(it->second); return SYG_OK; }
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
+    CK(cudaMalloc(&d, bytes));
+    if (!host.empty()) CK(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    ctx->tables[key] = d;
+    *out = reinterpret_cast<const T*>(d);
+    return SYG_OK;
+}
+
+std::string keyf(const char* fmt, ...) {
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return buf;
+}
+
+int get_fft_tables(syg_ctx* ctx, int n_fft, const float2** tw, const float2** tws) {
+    const int M = n_fft / 2;
+    std::string k1 = keyf("tw:%d", n_fft), k2 = keyf("tws:%d", n_fft);
+    std::vector<float2> a, b;
+    if (!ctx->tables.count(k1)) {
+        a.resize(M);
+        for (int k = 0; k < M; ++k) {
+            const double ang = -2.0 * sygplan::kPi * (double)k / (double)M;
+            a[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        b.resize(M / 2 + 1);
+        for (int k = 0; k <= M / 2; ++k) {
+            const double ang = -2.0 * sygplan::kPi * (double)k / (double)n_fft;
+            b[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+    }
+    int rc = upload_table(ctx, k1, a, tw);
+    if (rc) return rc;
+    return upload_table(ctx, k2, b, tws);
+}
+
+int get_window(syg_ctx* ctx, int window, int win_length, int n_fft, bool centred, const float** out) {
+    std::string key = keyf("win:%d:%d:%d:%d", window, win_length, n_fft, (int)centred);
+    std::vector<float> w;
+    if (!ctx->tables.count(key)) {
+        std::string err;
+        if (centred) {
+            if (!sygplan::build_window(window, win_length, n_fft, w, err)) return fail(SYG_E_BADARG, "%s", err.c_str());
+        } else {                                                    // scipy.signal.welch: window then zero padding
+            if (window < 0 || window > 3) return fail(SYG_E_UNSUPPORTED, "unsupported window id %d", window);
+            w.assign(n_fft, 0.0f);
+            for (int n = 0; n < win_length; ++n) w[n] = (float)sygplan::window_value_d(window, win_length, n);
+        }
+    }
+    return upload_table(ctx, key, w, out);
+}
+
+// ---------------------------------------------------------------------------------------------- kernel dispatch
+template <class TL, int MODE>
+int launch_frame_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
+    using SM = sygdev::FrameSmem<TL>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        CK(cudaFuncSetAttribute(sygdev::frame_kernel<TL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
+        int nb = 0;
+        CK(SYG_OCCUPANCY(nb, (sygdev::frame_kernel<TL, MODE>), sygdev::kThreads, SM::bytes));
+        if (nb < 1) return fail(SYG_E_CUDA, "frame kernel does not fit on an SM (smem %zu)", (size_t)SM::bytes);
+        blocks_per_sm = nb;
+    }
+    const long long n_rounds = (a.n_frames + TL::F - 1) / TL::F;
+    if (n_rounds <= 0) return SYG_OK;
+    const long long cap = (long long)sm_count * blocks_per_sm;
+    const int grid = (int)std::min<long long>(n_rounds, cap);
+    auto kfn = sygdev::frame_kernel<TL, MODE>;
+    SYG_LAUNCH(kfn, grid, sygdev::kThreads, SM::bytes, st, a);
+    CK(cudaGetLastError());
+    return SYG_OK;
+}
+
+template <int MODE>
+int launch_frame(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
+    using namespace sygdev;
+    switch (ilog2i(n_fft / 2)) {
+        case 4: return launch_frame_t<FftTile<4, 4>, MODE>(a, sm_count, st);
+        case 5: return launch_frame_t<FftTile<5, 8>, MODE>(a, sm_count, st);
+        case 6: return launch_frame_t<FftTile<6, 8>, MODE>(a, sm_count, st);
+        case 7: return launch_frame_t<FftTile<7, 16>, MODE>(a, sm_count, st);
+        case 8: return launch_frame_t<FftTile<8, 16>, MODE>(a, sm_count, st);
+        case 9: return launch_frame_t<FftTile<9, 16>, MODE>(a, sm_count, st);
+        case 10: return launch_frame_t<FftTile<10, 16>, MODE>(a, sm_count, st);
+        case 11: return launch_frame_t<FftTile<11, 16>, MODE>(a, sm_count, st);
+        case 12: return launch_frame_t<FftTile<12, 16>, MODE>(a, sm_count, st);
+    }
+    return fail(SYG_E_UNSUPPORTED, "n_fft=%d: only powers of two in [32, 8192] are supported", n_fft);
+}
+
+template <class TL>
+int launch_welch_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st) {
+    using SM = sygdev::WelchSmem<TL>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        CK(cudaFuncSetAttribute(sygdev::welch_kernel<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
+        int nb = 0;
+        CK(SYG_OCCUPANCY(nb, (sygdev::welch_kernel<TL>), sygdev::kThreads, SM::bytes));
+        if (nb < 1) return fail(SYG_E_CUDA, "welch kernel does not fit on an SM");
+        blocks_per_sm = nb;
+    }
+    if (a.g.n_units <= 0) return SYG_OK;
+    const int grid = (int)std::min<long long>(a.g.n_units, (long long)sm_count * blocks_per_sm);
+    auto kfn = sygdev::welch_kernel<TL>;
+    SYG_LAUNCH(kfn, grid, sygdev::kThreads, SM::bytes, st, a);
+    CK(cudaGetLastError());
+    return SYG_OK;
+}
+
+int launch_welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st) {
+    using namespace sygdev;
+    switch (ilog2i(nfft / 2)) {
+        case 4: return launch_welch_t<FftTile<4, 4>>(a, sm_count, st);
+        case 5: return launch_welch_t<FftTile<5, 8>>(a, sm_count, st);
+        case 6: return launch_welch_t<FftTile<6, 8>>(a, sm_count, st);
+        case 7: return launch_welch_t<FftTile<7, 16>>(a, sm_count, st);
+        case 8: return launch_welch_t<FftTile<8, 16>>(a, sm_count, st);
+        case 9: return launch_welch_t<FftTile<9, 16>>(a, sm_count, st);
+        case 10: return launch_welch_t<FftTile<10, 16>>(a, sm_count, st);
+        case 11: return launch_welch_t<FftTile<11, 16>>(a, sm_count, st);
+        case 12: return launch_welch_t<FftTile<12, 16>>(a, sm_count, st);
+    }
+    return fail(SYG_E_UNSUPPORTED, "nfft=%d: only powers of two in [32, 8192] are supported", nfft);
+}
+
+// ---------------------------------------------------------------------------------------------- validation
+int check_units(const syg_units* u) {
+    if (!u) return fail(SYG_E_BADARG, "units is NULL");
+    if (u->n_units < 0 || u->unit_len < 0 || u->total_len < 0) return fail(SYG_E_BADARG, "negative unit geometry");
+    if (!u->unit_starts && u->n_units > 1 && u->unit_stride < 0) return fail(SYG_E_BADARG, "negative unit_stride");
+    if (u->unit_len > 0x7fffffffLL) return fail(SYG_E_UNSUPPORTED, "unit_len above 2^31-1 samples");
+    return SYG_OK;
+}
+
+syg::UnitGeom geom_of(const syg_units* u, long long u0, long long n) {
+    syg::UnitGeom g;
+    g.n_units = n;
+    g.unit_len = u->unit_len;
+    g.unit_stride = u->unit_stride;
+    g.total_len = u->total_len;
+    g.unit_starts = u->unit_starts ? reinterpret_cast<const long long*>(u->unit_starts) + u0 : nullptr;
+    g.unit_valid = u->unit_valid ? u->unit_valid + u0 : nullptr;
+    g.unit0 = u0;
+    return g;
+}
+
+struct FeaturePlan {
+    syg::FrameArgs fa;             // everything except y, geometry, out, workspaces
+    syg::FinalizeArgs fin;
+    int n_rows = 0;
+    int T = 0;
+    size_t ws_per_unit = 0;        // bytes of melws + cws per unit
+};
+
+int rows_of(const syg_feature_params* p, int32_t* n_rows) {
+    if (!p || !n_rows) return fail(SYG_E_BADARG, "NULL argument");
+    if (p->n_features < 0 || p->n_features > SYG_MAX_FEATURES) return fail(SYG_E_BADARG, "n_features out of range");
+    int rows = 0;
+    unsigned seen = 0;
+    for (int i = 0; i < p->n_features; ++i) {
+        const int f = p->features[i];
+        if (f < 0 || f >= SYG_FEAT_COUNT_) return fail(SYG_E_BADARG, "unknown feature id %d", f);
+        if (seen & (1u << f)) return fail(SYG_E_BADARG, "feature id %d requested twice", f);
+        seen |= 1u << f;
+        if (f == SYG_FEAT_MFCC) rows += p->n_mfcc;
+        else if (f == SYG_FEAT_SPECTRAL_CONTRAST) rows += p->contrast_n_bands + 1;
+        else rows += 1;
+    }
+    *n_rows = rows;
+    return SYG_OK;
+}
+
+int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_params* p, FeaturePlan& pl) {
+    if (!p) return fail(SYG_E_BADARG, "params is NULL");
+    if (p->sr <= 0) return fail(SYG_E_BADARG, "sr must be positive");
+    const int fl = p->frame_length;
+    if (!is_pow2(fl) || fl < 32 || fl > 8192)
+        return fail(SYG_E_UNSUPPORTED, "frame_length=%d: only powers of two in [32, 8192] are supported", fl);
+    if (p->hop_length < 1) return fail(SYG_E_BADARG, "hop_length must be >= 1");
+    int32_t rows = 0;
+    int rc = rows_of(p, &rows);
+    if (rc) return rc;
+    std::memset(&pl.fa, 0, sizeof(pl.fa));
+    std::memset(&pl.fin, 0, sizeof(pl.fin));
+    syg::FrameArgs& a = pl.fa;
+    a.row_centroid = a.row_rolloff = a.row_rms = a.row_crest = a.row_peak = a.row_bandwidth = a.row_flatness =
+        a.row_dominant = a.row_zcr = a.row_mean_amp = a.row_std_amp = -1;
+    pl.fin.row_mfcc = -1;
+    pl.fin.row_contrast = -1;
+    int row = 0;
+    unsigned mask = 0;
+    for (int i = 0; i < p->n_features; ++i) {
+        switch (p->features[i]) {
+            case SYG_FEAT_MFCC: mask |= syg::FB_MFCC; pl.fin.row_mfcc = row; row += p->n_mfcc; break;
+            case SYG_FEAT_SPECTRAL_CONTRAST: mask |= syg::FB_CONTRAST; pl.fin.row_contrast = row; row += p->contrast_n_bands + 1; break;
+            case SYG_FEAT_SPECTRAL_CENTROID: mask |= syg::FB_CENTROID; a.row_centroid = row++; break;
+            case SYG_FEAT_SPECTRAL_ROLLOFF: mask |= syg::FB_ROLLOFF; a.row_rolloff = row++; break;
+            case SYG_FEAT_RMS_ENERGY: mask |= syg::FB_RMS; a.row_rms = row++; break;
+            case SYG_FEAT_CREST_FACTOR: mask |= syg::FB_CREST; a.row_crest = row++; break;
+            case SYG_FEAT_PEAK_AMPLITUDE: mask |= syg::FB_PEAK; a.row_peak = row++; break;
+            case SYG_FEAT_SPECTRAL_BANDWIDTH: mask |= syg::FB_BANDWIDTH; a.row_bandwidth = row++; break;
+            case SYG_FEAT_SPECTRAL_FLATNESS: mask |= syg::FB_FLATNESS; a.row_flatness = row++; break;
+            case SYG_FEAT_DOMINANT_FREQUENCY: mask |= syg::FB_DOMINANT; a.row_dominant = row++; break;
+            case SYG_FEAT_MEAN_AMPLITUDE: mask |= syg::FB_MEAN_AMP; a.row_mean_amp = row++; break;
+            case SYG_FEAT_STD_DEV_AMPLITUDE: mask |= syg::FB_STD_AMP; a.row_std_amp = row++; break;
+        }
+    }
+    a.mask = mask;
+    a.n_rows = rows;
+    pl.n_rows = rows;
+    const long long T = syg_frame_count(u->unit_len, fl, p->hop_length, p->center);
+    if (T > 0x7fffffffLL) return fail(SYG_E_UNSUPPORTED, "too many frames per unit");
+    pl.T = (int)T;
+    a.T = (int)T;
+    a.hop = p->hop_length;
+    a.cpad = p->center ? fl / 2 : 0;
+    a.pad_mode = 0;
+    a.bin_hz = sygplan::bin_hz((double)p->sr, fl);
+    a.roll_percent = p->roll_percent;
+    rc = get_window(ctx, p->window, fl, fl, true, &a.window);
+    if (rc) return rc;
+    rc = get_fft_tables(ctx, fl, &a.tw, &a.tws);
+    if (rc) return rc;
+    size_t ws = 0;
+    if (mask & syg::FB_MFCC) {
+        if (p->n_mels < 1 || p->n_mels > 256) return fail(SYG_E_UNSUPPORTED, "n_mels=%d: supported range is [1, 256]", p->n_mels);
+        if (p->n_mfcc < 1 || p->n_mfcc > p->n_mels) return fail(SYG_E_BADARG, "n_mfcc must be in [1, n_mels]");
+        if (!(p->power > 0.0)) return fail(SYG_E_BADARG, "power must be positive");
+        const double fmax = p->fmax > 0 ? (double)p->fmax : 0.5 * (double)p->sr;
+        std::string key = keyf("mel:%d:%d:%d:%.9g:%.9g", p->sr, fl, p->n_mels, (double)p->fmin, fmax);
+        sygplan::MelTable mt;
+        if (!ctx->tables.count(key + ":w")) {
+            std::string err;
+            if (!sygplan::build_mel((double)p->sr, fl, p->n_mels, (double)p->fmin, fmax, false, mt, err))
+                return fail(SYG_E_BADARG, "%s", err.c_str());
+        }
+        if ((rc = upload_table(ctx, key + ":s", mt.start, &a.mel_start))) return rc;
+        if ((rc = upload_table(ctx, key + ":l", mt.len, &a.mel_len))) return rc;
+        if ((rc = upload_table(ctx, key + ":o", mt.off, &a.mel_off))) return rc;
+        if ((rc = upload_table(ctx, key + ":w", mt.w, &a.mel_w))) return rc;
+        a.n_mels = p->n_mels;
+        a.mel_power_is_2 = (p->power == 2.0);
+        a.mel_half_power = (float)(0.5 * p->power);
+        std::string dk = keyf("dct:%d:%d:%d:%d:%.9g", p->n_mfcc, p->n_mels, p->dct_type, p->dct_ortho, (double)p->lifter);
+        std::vector<float> dct;
+        if (!ctx->tables.count(dk)) {
+            std::string err;
+            if (!sygplan::build_dct(p->n_mfcc, p->n_mels, p->dct_type, p->dct_ortho != 0, (double)p->lifter, p->n_mfcc, dct, err))
+                return fail(SYG_E_BADARG, "%s", err.c_str());
+        }
+        if ((rc = upload_table(ctx, dk, dct, &pl.fin.dct))) return rc;
+        pl.fin.n_mels = p->n_mels;
+        pl.fin.n_mfcc = p->n_mfcc;
+        ws += (size_t)T * p->n_mels * sizeof(float);
+    }
+    if (mask & syg::FB_CONTRAST) {
+        sygplan::Bands b;
+        std::string err;
+        if (!sygplan::build_bands((double)p->sr, fl, p->contrast_n_bands, (double)p->contrast_fmin,
+                                  (double)p->contrast_quantile, b, err))
+            return fail(SYG_E_BADARG, "%s", err.c_str());
+        a.nb = b.nb;
+        for (int i = 0; i < b.nb; ++i) { a.band_lo[i] = b.lo[i]; a.band_cnt[i] = b.cnt[i]; a.band_n[i] = b.nq[i]; }
+        pl.fin.nb = b.nb;
+        ws += (size_t)T * 2 * b.nb * sizeof(float);
+    }
+    pl.ws_per_unit = ws + 4 * sizeof(unsigned);
+    pl.fin.T = (int)T;
+    pl.fin.n_rows = rows;
+    pl.fin.amin = 1e-10f;
+    pl.fin.top_db = 80.0f;
+    return SYG_OK;
+}
+
+// run the two kernels for units [0, n) of geometry g, writing out rows for those units
+int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, const syg::UnitGeom& g, float* out,
+                       void* ws, int n_fft, cudaStream_t st) {
+    syg::FrameArgs a = pl.fa;
+    a.y = y;
+    a.g = g;
+    a.n_frames = g.n_units * (long long)pl.T;
+    a.out = out;
+    char* w = reinterpret_cast<char*>(ws);
+    a.unit_max = reinterpret_cast<unsigned*>(w);
+    size_t off = ((size_t)g.n_units * 4 * sizeof(unsigned) + 255) / 256 * 256;
+    a.melws = reinterpret_cast<float*>(w + off);
+    off += ((size_t)a.n_frames * pl.fin.n_mels * sizeof(float) + 255) / 256 * 256;
+    a.cws = reinterpret_cast<float*>(w + off);
+    const bool need_fin = (a.mask & (syg::FB_MFCC | syg::FB_CONTRAST)) != 0;
+    if (need_fin) CK(cudaMemsetAsync(a.unit_max, 0, (size_t)g.n_units * 4 * sizeof(unsigned), st));
+    int rc;
+    {
+        ProfScope ps(ctx, st, PROF_FRAME);
+        rc = launch_frame<sygdev::MODE_FEATURES>(n_fft, a, ctx->sm_count, st);
+    }
+    if (rc) return rc;
+    if (need_fin) {
+        ProfScope ps(ctx, st, PROF_FINALIZE);
+        syg::FinalizeArgs f = pl.fin;
+        f.n_units = g.n_units;
+        f.melws = a.melws;
+        f.cws = a.cws;
+        f.unit_max = a.unit_max;
+        f.out = out;
+        const int gx = (pl.T + sygdev::kFinTT - 1) / sygdev::kFinTT;
+        const size_t smem = (size_t)sygdev::kFinTT * (f.n_mels + 1) * sizeof(float);
+        for (long long u0 = 0; u0 < g.n_units; u0 += 65535) {       // gridDim.y limit
+            syg::FinalizeArgs fc = f;
+            fc.n_units = std::min<long long>(65535, g.n_units - u0);
+            fc.melws = f.melws + (size_t)u0 * pl.T * f.n_mels;
+            fc.cws = f.cws + (size_t)u0 * pl.T * 2 * f.nb;
+            fc.unit_max = f.unit_max + u0 * 4;
+            fc.out = out + (size_t)u0 * pl.n_rows * pl.T;
+            dim3 grid((unsigned)gx, (unsigned)fc.n_units);
+            SYG_LAUNCH(sygdev::finalize_kernel, grid, dim3(sygdev::kThreads), smem, st, fc);
+            CK(cudaGetLastError());
+        }
+    }
+    return SYG_OK;
+}
+
+size_t features_ws_bytes(const FeaturePlan& pl, long long n) {
+    size_t b = ((size_t)n * 4 * sizeof(unsigned) + 255) / 256 * 256;
+    b += ((size_t)n * pl.T * pl.fin.n_mels * sizeof(float) + 255) / 256 * 256;
+    b += ((size_t)n * pl.T * 2 * pl.fin.nb * sizeof(float) + 255) / 256 * 256;
+    return b + 256;
+}
+
+// ---------------------------------------------------------------------------------------------- host pipelines
+struct HostChunk {
+    long long u0, n;               // units of the chunk
+    long long begin, end;          // sample range of y_host covered by the chunk
+};
+
+// sample range needed by units [u0, u0 + n)
+void chunk_range(const syg_units* u, long long u0, long long n, long long* begin, long long* end) {
+    if (!u->unit_starts) {
+        long long b = u0 * u->unit_stride;
+        long long e = (u0 + n - 1) * u->unit_stride + u->unit_len;
+        b = std::min(std::max(b, 0LL), (long long)u->total_len);
+        e = std::min(std::max(e, b), (long long)u->total_len);
+        *begin = b; *end = e;
+        return;
+    }
+    long long b = u->total_len, e = 0;
+    for (long long i = u0; i < u0 + n; ++i) {
+        const long long s = u->unit_starts[i];
+        long long v = u->unit_valid ? u->unit_valid[i] : u->total_len - s;
+        v = std::min<long long>(std::max<long long>(v, 0), u->unit_len);
+        if (v > 0) { b = std::min(b, s); e = std::max(e, s + v); }
+    }
+    if (e < b) { b = 0; e = 0; }
+    *begin = b; *end = e;
+}
+
+int check_host_units(const syg_units* u) {
+    int rc = check_units(u);
+    if (rc) return rc;
+    if (u->unit_starts) {
+        for (long long i = 0; i < u->n_units; ++i) {
+            const long long s = u->unit_starts[i];
+            long long v = u->unit_valid ? u->unit_valid[i] : u->total_len - s;
+            v = std::min<long long>(std::max<long long>(v, 0), u->unit_len);
+            if (s < 0 || s + v > u->total_len) return fail(SYG_E_BADARG, "unit %lld lies outside the sample buffer", i);
+        }
+    }
+    return SYG_OK;
+}
+
+// Generic chunked host pipeline: H2D of the chunk's samples, `run` on the lane's stream, D2H of up to two outputs.
+template <class Run>
+int host_pipeline(syg_ctx* ctx, const float* y_host, const syg_units* u, size_t out0_per_unit, void* out0_host,
+                  size_t out1_per_unit, void* out1_host, size_t ws_per_unit, long long max_chunk_units, Run run) {
+    if (u->n_units == 0) return SYG_OK;
+    const size_t in_target = (size_t)128 << 20, out_target = (size_t)256 << 20;
+    long long span = u->unit_starts ? u->unit_len : std::max<long long>(1, std::min(u->unit_stride, u->unit_len));
+    long long chunk = std::max<long long>(1, (long long)(in_target / (std::max<long long>(span, 1) * sizeof(float))));
+    if (out0_per_unit + out1_per_unit) chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(out_target / (out0_per_unit + out1_per_unit))));
+    if (ws_per_unit) chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(ctx->ws_limit / ws_per_unit)));
+    chunk = std::min(chunk, max_chunk_units);
+    if (u->n_units > 1) chunk = std::min<long long>(chunk, (u->n_units + 1) / 2);           // keep both lanes busy
+    chunk = std::max<long long>(chunk, 1);
+    for (int l = 0; l < 2; ++l)
+        if (!ctx->lanes[l].stream) CK(cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking));
+    int li = 0;
+    std::vector<long long> rel;
+    std::vector<int> val;
+    for (long long u0 = 0; u0 < u->n_units; u0 += chunk, li ^= 1) {
+        const long long n = std::min(chunk, u->n_units - u0);
+        Lane& L = ctx->lanes[li];
+        long long b, e;
+        chunk_range(u, u0, n, &b, &e);
+        int rc;
+        if ((rc = L.in.ensure(std::max<size_t>((size_t)(e - b) * sizeof(float), 256)))) return rc;
+        if ((rc = L.out0.ensure(std::max<size_t>(out0_per_unit * n, 256)))) return rc;
+        if (out1_per_unit && (rc = L.out1.ensure(out1_per_unit * n))) return rc;
+        if (ws_per_unit && (rc = L.ws.ensure(ws_per_unit * n + 4096))) return rc;
+        // the lane's previous chunk must have left its buffers (same stream => ordered); host-side staging
+        // vectors are reused, so wait for the previous upload of this lane's tables
+        if (e > b) CK(cudaMemcpyAsync(L.in.p, y_host + b, (size_t)(e - b) * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        syg_units cu;
+        cu.n_units = n;
+        cu.unit_len = u->unit_len;
+        cu.unit_starts = nullptr;
+        cu.unit_valid = nullptr;
+        if (!u->unit_starts) {
+            // analytic starts continue inside the chunk: unit i of the chunk starts at (u0+i)*stride - b
+            cu.unit_stride = u->unit_stride;
+            cu.total_len = e - b;
+        } else {
+            rel.resize(n);
+            val.resize(n);
+            for (long long i = 0; i < n; ++i) {
+                const long long s = u->unit_starts[u0 + i];
+                long long v = u->unit_valid ? u->unit_valid[u0 + i] : u->total_len - s;
+                v = std::min<long long>(std::max<long long>(v, 0), u->unit_len);
+                rel[i] = v > 0 ? s - b : 0;
+                val[i] = (int)v;
+            }
+            if ((rc = L.starts.ensure(n * sizeof(long long)))) return rc;
+            if ((rc = L.valid.ensure(n * sizeof(int)))) return rc;
+            CK(cudaMemcpyAsync(L.starts.p, rel.data(), n * sizeof(long long), cudaMemcpyHostToDevice, L.stream));
+            CK(cudaMemcpyAsync(L.valid.p, val.data(), n * sizeof(int), cudaMemcpyHostToDevice, L.stream));
+            CK(cudaStreamSynchronize(L.stream));                      // rel/val are reused by the next chunk
+            cu.unit_stride = 0;
+            cu.total_len = e - b;
+            cu.unit_starts = reinterpret_cast<const int64_t*>(L.starts.p);
+            cu.unit_valid = reinterpret_cast<const int32_t*>(L.valid.p);
+        }
+        // analytic chunks: the kernel computes start = (u + unit0) * stride; shift the base pointer instead
+        const float* y_dev = reinterpret_cast<const float*>(L.in.p);
+        long long shift = 0;
+        if (!u->unit_starts) shift = u0 * u->unit_stride - b;        // >= 0: first unit's start relative to the chunk
+        rc = run(L, y_dev, cu, shift, u0, n);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(reinterpret_cast<char*>(out0_host) + (size_t)u0 * out0_per_unit, L.out0.p, out0_per_unit * n,
+                           cudaMemcpyDeviceToHost, L.stream));
+        if (out1_per_unit && out1_host)
+            CK(cudaMemcpyAsync(reinterpret_cast<char*>(out1_host) + (size_t)u0 * out1_per_unit, L.out1.p, out1_per_unit * n,
+                               cudaMemcpyDeviceToHost, L.stream));
+    }
+    for (int l = 0; l < 2; ++l) CK(cudaStreamSynchronize(ctx->lanes[l].stream));
+    return SYG_OK;
+}
+
+// geometry of a host chunk on the device: analytic chunks keep (unit0 = 0) and fold the offset into the pointer
+syg::UnitGeom chunk_geom(const syg_units& cu, long long shift) {
+    syg::UnitGeom g;
+    g.n_units = cu.n_units;
+    g.unit_len = cu.unit_len;
+    g.unit_stride = cu.unit_stride;
+    g.total_len = cu.total_len - shift;     // samples available from the (shifted) base
+    g.unit_starts = reinterpret_cast<const long long*>(cu.unit_starts);
+    g.unit_valid = cu.unit_valid;
+    g.unit0 = 0;
+    return g;
+}
+
+int stft_setup(syg_ctx* ctx, const syg_units* u, int n_fft, int hop, int win_length, int window, int center, int pad_mode,
+               int out_kind, syg::FrameArgs& a) {
+    if (!is_pow2(n_fft) || n_fft < 32 || n_fft > 8192)
+        return fail(SYG_E_UNSUPPORTED, "n_fft=%d: only powers of two in [32, 8192] are supported", n_fft);
+    if (hop < 1) return fail(SYG_E_BADARG, "hop_length must be >= 1");
+    if (win_length < 1 || win_length > n_fft) return fail(SYG_E_BADARG, "win_length must be in [1, n_fft]");
+    if (pad_mode != SYG_PAD_CONSTANT && pad_mode != SYG_PAD_REFLECT) return fail(SYG_E_UNSUPPORTED, "unsupported pad_mode %d", pad_mode);
+    if (out_kind < 0 || out_kind > 2) return fail(SYG_E_BADARG, "unknown out_kind %d", out_kind);
+    if (center && pad_mode == SYG_PAD_REFLECT && u->unit_len <= n_fft / 2 && u->unit_len > 0)
+        return fail(SYG_E_SHAPE, "reflect padding needs unit_len > n_fft/2");
+    std::memset(&a, 0, sizeof(a));
+    const long long T = syg_frame_count(u->unit_len, n_fft, hop, center);
+    if (T > 0x7fffffffLL) return fail(SYG_E_UNSUPPORTED, "too many frames per unit");
+    a.T = (int)T;
+    a.hop = hop;
+    a.cpad = center ? n_fft / 2 : 0;
+    a.pad_mode = center ? pad_mode : 0;
+    a.out_kind = out_kind;
+    int rc = get_window(ctx, window, win_length, n_fft, true, &a.window);
+    if (rc) return rc;
+    return get_fft_tables(ctx, n_fft, &a.tw, &a.tws);
+}
+
+struct WelchPlan {
+    syg::WelchArgs wa;
+    int nfft = 0;
+};
+
+int welch_setup(syg_ctx* ctx, const syg_units* u, double fs, int window, int nperseg, int noverlap, int nfft, int detrend,
+                int scaling, WelchPlan& pl) {
+    if (!(fs > 0)) return fail(SYG_E_BADARG, "fs must be positive");
+    if (nperseg < 1) return fail(SYG_E_BADARG, "nperseg must be >= 1");
+    if (nfft <= 0) nfft = nperseg;
+    if (noverlap < 0) noverlap = nperseg / 2;
+    if (noverlap >= nperseg) return fail(SYG_E_BADARG, "noverlap must be less than nperseg.");
+    if (nfft < nperseg) return fail(SYG_E_BADARG, "nfft must be greater than or equal to nperseg.");
+    if (!is_pow2(nfft) || nfft < 32 || nfft > 8192)
+        return fail(SYG_E_UNSUPPORTED, "nfft=%d: only powers of two in [32, 8192] are supported", nfft);
+    if (u->unit_len < nperseg) return fail(SYG_E_SHAPE, "unit_len=%lld shorter than nperseg=%d", (long long)u->unit_len, nperseg);
+    if (scaling != SYG_SCALING_DENSITY && scaling != SYG_SCALING_SPECTRUM) return fail(SYG_E_BADARG, "unknown scaling %d", scaling);
+    if (window < 0 || window > 3) return fail(SYG_E_UNSUPPORTED, "unsupported window id %d", window);
+    std::memset(&pl.wa, 0, sizeof(pl.wa));
+    syg::WelchArgs& a = pl.wa;
+    pl.nfft = nfft;
+    a.nperseg = nperseg;
+    a.step = nperseg - noverlap;
+    a.nseg = (int)((u->unit_len - noverlap) / a.step);
+    a.detrend = detrend ? 1 : 0;
+    double s1 = 0.0, s2 = 0.0;
+    for (int n = 0; n < nperseg; ++n) { const double w = sygplan::window_value_d(window, nperseg, n); s1 += w; s2 += w * w; }
+    a.scale = (float)(scaling == SYG_SCALING_DENSITY ? 1.0 / (fs * s2) : 1.0 / (s1 * s1));
+    a.onesided_double = 1;
+    int rc = get_window(ctx, window, nperseg, nfft, false, &a.window);
+    if (rc) return rc;
+    return get_fft_tables(ctx, nfft, &a.tw, &a.tws);
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* syg_version(void) {
+#ifdef SYG_EMU
+    return "sygb200 0.1.0 (emulator test build)";
+#else
+    return "sygb200 0.1.0 (sm_100a)";
+#endif
+}
+
+const char* syg_last_error(void) { return g_err.c_str(); }
+
+int syg_ctx_create(int device, syg_ctx** out) {
+    if (!out) return fail(SYG_E_BADARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(SYG_E_CUDA, "no CUDA device available (%s); sygb200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(SYG_E_BADARG, "device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    syg_ctx* c = new syg_ctx();
+    c->device = device;
+    e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess || c->sm_count <= 0) { delete c; return fail(SYG_E_CUDA, "cannot query SM count"); }
+    *out = c;
+    return SYG_OK;
+}
+
+void syg_ctx_destroy(syg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->tables) cudaFree(kv.second);
+    ctx->ws.release();
+    for (auto& l : ctx->lanes) {
+        l.in.release(); l.out0.release(); l.out1.release(); l.starts.release(); l.valid.release(); l.ws.release();
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
+    delete ctx;
+}
+
+int syg_ctx_set_workspace_limit(syg_ctx* ctx, size_t bytes) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    if (bytes < ((size_t)1 << 20)) return fail(SYG_E_BADARG, "workspace limit below 1 MiB");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->ws_limit = bytes;
+    return SYG_OK;
+}
+
+int syg_ctx_sm_count(const syg_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int syg_ctx_profile_enable(syg_ctx* ctx, int on) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->prof_on = on != 0;
+    return SYG_OK;
+}
+
+int syg_ctx_profile_read(syg_ctx* ctx, double* ms, int64_t* launches, int reset) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    for (auto& pp : ctx->prof_pairs) {
+        float t = 0.0f;
+        CK(cudaEventSynchronize(pp.b));
+        CK(cudaEventElapsedTime(&t, pp.a, pp.b));
+        ctx->prof_ms[pp.kind] += (double)t;
+        ctx->prof_n[pp.kind] += 1;
+        cudaEventDestroy(pp.a);
+        cudaEventDestroy(pp.b);
+    }
+    ctx->prof_pairs.clear();
+    for (int i = 0; i < 3; ++i) {
+        if (ms) ms[i] = ctx->prof_ms[i];
+        if (launches) launches[i] = ctx->prof_n[i];
+        if (reset) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+    }
+    return SYG_OK;
+}
+
+void syg_feature_params_default(syg_feature_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->sr = 22050;
+    p->frame_length = 2048;       // manager.py:82
+    p->hop_length = 512;          // manager.py:83
+    p->center = 1;
+    p->window = SYG_WINDOW_HANN;
+    p->n_mels = 128;              // manager.py:214
+    p->fmin = 0.0;
+    p->fmax = 0.0;
+    p->power = 2.0;
+    p->n_mfcc = 13;               // cepstral.py:24
+    p->dct_type = 2;
+    p->dct_ortho = 1;
+    p->lifter = 0.0;
+    p->contrast_n_bands = 6;      // frequency_domain.py:150
+    p->contrast_fmin = 200.0;
+    p->contrast_quantile = 0.02;
+    p->roll_percent = 0.85;      // frequency_domain.py:277
+}
+
+int syg_features_rows(const syg_feature_params* p, int32_t* n_rows) { return rows_of(p, n_rows); }
+
+int64_t syg_frame_count(int64_t n_samples, int32_t frame_length, int32_t hop_length, int32_t center) {
+    if (hop_length < 1 || frame_length < 1 || n_samples < 0) return 0;
+    int64_t n = n_samples;
+    if (center) n += 2 * (int64_t)(frame_length / 2);
+    if (n < frame_length) return 0;
+    return 1 + (n - frame_length) / hop_length;
+}
+
+int syg_features_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, const syg_feature_params* p,
+                     float* out_dev, void* stream) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    int rc = check_units(units);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    FeaturePlan pl;
+    if ((rc = build_feature_plan(ctx, units, p, pl))) return rc;
+    if (units->n_units == 0 || pl.T <= 0 || pl.n_rows == 0) return SYG_OK;
+    if (!y_dev && units->total_len > 0) return fail(SYG_E_BADARG, "y_dev is NULL");
+    if (!out_dev) return fail(SYG_E_BADARG, "out_dev is NULL");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long chunk = std::max<long long>(1, (long long)(ctx->ws_limit / std::max<size_t>(pl.ws_per_unit, 1)));
+    chunk = std::min<long long>(chunk, units->n_units);
+    if ((rc = ctx->ws.ensure(features_ws_bytes(pl, chunk)))) return rc;
+    for (long long u0 = 0; u0 < units->n_units; u0 += chunk) {
+        const long long n = std::min(chunk, units->n_units - u0);
+        syg::UnitGeom g = geom_of(units, u0, n);
+        rc = run_features_chunk(ctx, pl, y_dev, g, out_dev + (size_t)u0 * pl.n_rows * pl.T, ctx->ws.p, p->frame_length, st);
+        if (rc) return rc;
+    }
+    return SYG_OK;
+}
+
+int syg_features_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, const syg_feature_params* p,
+                          float* out_host) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    int rc = check_host_units(units);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    FeaturePlan pl;
+    if ((rc = build_feature_plan(ctx, units, p, pl))) return rc;
+    if (units->n_units == 0 || pl.T <= 0 || pl.n_rows == 0) return SYG_OK;
+    if (!y_host && units->total_len > 0) return fail(SYG_E_BADARG, "y_host is NULL");
+    if (!out_host) return fail(SYG_E_BADARG, "out_host is NULL");
+    const size_t out_per_unit = (size_t)pl.n_rows * pl.T * sizeof(float);
+    const int n_fft = p->frame_length;
+    return host_pipeline(ctx, y_host, units, out_per_unit, out_host, 0, nullptr, features_ws_bytes(pl, 1), 1LL << 40,
+                         [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long n) -> int {
+                             int r = L.ws.ensure(features_ws_bytes(pl, n));
+                             if (r) return r;
+                             syg::UnitGeom g = chunk_geom(cu, shift);
+                             return run_features_chunk(ctx, pl, y_dev + shift, g, reinterpret_cast<float*>(L.out0.p), L.ws.p,
+                                                       n_fft, L.stream);
+                         });
+}
+
+static size_t stft_elem_bytes(int out_kind) { return out_kind == SYG_OUT_COMPLEX ? 2 * sizeof(float) : sizeof(float); }
+
+int syg_stft_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, int32_t n_fft, int32_t hop_length,
+                 int32_t win_length, int32_t window, int32_t center, int32_t pad_mode, int32_t out_kind,
+                 void* out_dev, void* stream) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    int rc = check_units(units);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    syg::FrameArgs a;
+    if ((rc = stft_setup(ctx, units, n_fft, hop_length, win_length, window, center, pad_mode, out_kind, a))) return rc;
+    if (units->n_units == 0 || a.T <= 0) return SYG_OK;
+    if (!y_dev && units->total_len > 0) return fail(SYG_E_BADARG, "y_dev is NULL");
+    if (!out_dev) return fail(SYG_E_BADARG, "out_dev is NULL");
+    a.y = y_dev;
+    a.g = geom_of(units, 0, units->n_units);
+    a.n_frames = units->n_units * (long long)a.T;
+    a.stft_out = out_dev;
+    ProfScope ps(ctx, reinterpret_cast<cudaStream_t>(stream), PROF_FRAME);
+    return launch_frame<sygdev::MODE_STFT>(n_fft, a, ctx->sm_count, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, int32_t n_fft, int32_t hop_length,
+                      int32_t win_length, int32_t window, int32_t center, int32_t pad_mode, int32_t out_kind,
+                      void* out_host) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    int rc = check_host_units(units);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    syg::FrameArgs a;
+    if ((rc = stft_setup(ctx, units, n_fft, hop_length, win_length, window, center, pad_mode, out_kind, a))) return rc;
+    if (units->n_units == 0 || a.T <= 0) return SYG_OK;
+    if (!y_host && units->total_len > 0) return fail(SYG_E_BADARG, "y_host is NULL");
+    if (!out_host) return fail(SYG_E_BADARG, "out_host is NULL");
+    const size_t out_per_unit = (size_t)(n_fft / 2 + 1) * a.T * stft_elem_bytes(out_kind);
+    const int sm = ctx->sm_count;
+    return host_pipeline(ctx, y_host, units, out_per_unit, out_host, 0, nullptr, 0, 1LL << 40,
+                         [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long n) -> int {
+                             syg::FrameArgs c = a;
+                             c.y = y_dev + shift;
+                             c.g = chunk_geom(cu, shift);
+                             c.n_frames = n * (long long)a.T;
+                             c.stft_out = L.out0.p;
+                             return launch_frame<sygdev::MODE_STFT>(n_fft, c, sm, L.stream);
+                         });
+}
+
+int syg_psd_welch_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, double fs, int32_t window,
+                      int32_t nperseg, int32_t noverlap, int32_t nfft, int32_t detrend_constant, int32_t scaling,
+                      float* psd_dev, float* stats_dev, void* stream) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    int rc = check_units(units);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    WelchPlan pl;
+    if ((rc = welch_setup(ctx, units, fs, window, nperseg, noverlap, nfft, detrend_constant, scaling, pl))) return rc;
+    if (units->n_units == 0) return SYG_OK;
+    if (!y_dev || !psd_dev) return fail(SYG_E_BADARG, "NULL device pointer");
+    pl.wa.y = y_dev;
+    pl.wa.g = geom_of(units, 0, units->n_units);
+    pl.wa.psd = psd_dev;
+    pl.wa.stats = stats_dev;
+    ProfScope ps(ctx, reinterpret_cast<cudaStream_t>(stream), PROF_WELCH);
+    return launch_welch(pl.nfft, pl.wa, ctx->sm_count, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int syg_psd_welch_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, double fs, int32_t window,
+                           int32_t nperseg, int32_t noverlap, int32_t nfft, int32_t detrend_constant,
+                           int32_t scaling, float* psd_host, float* stats_host) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    int rc = check_host_units(units);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    WelchPlan pl;
+    if ((rc = welch_setup(ctx, units, fs, window, nperseg, noverlap, nfft, detrend_constant, scaling, pl))) return rc;
+    if (units->n_units == 0) return SYG_OK;
+    if (!y_host || !psd_host) return fail(SYG_E_BADARG, "NULL host pointer");
+    const size_t psd_per_unit = (size_t)(pl.nfft / 2 + 1) * sizeof(float);
+    const size_t st_per_unit = stats_host ? 3 * sizeof(float) : 0;
+    const int sm = ctx->sm_count;
+    return host_pipeline(ctx, y_host, units, psd_per_unit, psd_host, st_per_unit, stats_host, 0, 1LL << 40,
+                         [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long) -> int {
+                             syg::WelchArgs c = pl.wa;
+                             c.y = y_dev + shift;
+                             c.g = chunk_geom(cu, shift);
+                             c.psd = reinterpret_cast<float*>(L.out0.p);
+                             c.stats = st_per_unit ? reinterpret_cast<float*>(L.out1.p) : nullptr;
+                             return launch_welch(pl.nfft, c, sm, L.stream);
+                         });
+}
+
+int64_t syg_segment_count(int64_t total_samples, double sr, double segment_length_sec, double overlap_ratio,
+                          int32_t pad, double min_segment_length_sec, int64_t* seg_len, int64_t* seg_hop) {
+    std::string err;
+    int64_t n = sygplan::segment_table(total_samples, sr, segment_length_sec, overlap_ratio, pad != 0,
+                                       min_segment_length_sec, seg_len, seg_hop, nullptr, nullptr, 0, err);
+    if (n < 0) return fail(SYG_E_BADARG, "%s", err.c_str());
+    return n;
+}
+
+int64_t syg_segment_table(int64_t total_samples, double sr, double segment_length_sec, double overlap_ratio,
+                          int32_t pad, double min_segment_length_sec, int64_t* starts, int32_t* valid, int64_t cap) {
+    std::string err;
+    int64_t n = sygplan::segment_table(total_samples, sr, segment_length_sec, overlap_ratio, pad != 0,
+                                       min_segment_length_sec, nullptr, nullptr, starts, valid, cap, err);
+    if (n < 0) return fail(SYG_E_BADARG, "%s", err.c_str());
+    return n;
+}
+
+int syg_debug_window(int32_t window, int32_t win_length, int32_t n_fft, float* out) {
+    if (!out) return fail(SYG_E_BADARG, "out is NULL");
+    std::vector<float> w;
+    std::string err;
+    if (!sygplan::build_window(window, win_length, n_fft, w, err)) return fail(SYG_E_BADARG, "%s", err.c_str());
+    std::memcpy(out, w.data(), w.size() * sizeof(float));
+    return SYG_OK;
+}
+
+int syg_debug_mel_basis(int32_t sr, int32_t n_fft, int32_t n_mels, double fmin, double fmax, float* out) {
+    if (!out) return fail(SYG_E_BADARG, "out is NULL");
+    sygplan::MelTable mt;
+    std::string err;
+    if (!sygplan::build_mel((double)sr, n_fft, n_mels, (double)fmin, fmax > 0 ? (double)fmax : 0.5 * sr, true, mt, err))
+        return fail(SYG_E_BADARG, "%s", err.c_str());
+    std::memcpy(out, mt.dense.data(), mt.dense.size() * sizeof(float));
+    return SYG_OK;
+}
+
+int syg_debug_dct(int32_t n_mfcc, int32_t n_mels, int32_t dct_type, int32_t ortho, double lifter, float* out) {
+    if (!out) return fail(SYG_E_BADARG, "out is NULL");
+    std::vector<float> d;
+    std::string err;
+    if (!sygplan::build_dct(n_mfcc, n_mels, dct_type, ortho != 0, (double)lifter, n_mfcc, d, err))
+        return fail(SYG_E_BADARG, "%s", err.c_str());
+    std::memcpy(out, d.data(), d.size() * sizeof(float));
+    return SYG_OK;
+}
+
+int syg_debug_contrast_bands(int32_t sr, int32_t n_fft, int32_t n_bands, double fmin, double quantile, int32_t* lo,
+                             int32_t* cnt, int32_t* nq) {
+    sygplan::Bands b;
+    std::string err;
+    if (!sygplan::build_bands((double)sr, n_fft, n_bands, (double)fmin, (double)quantile, b, err))
+        return fail(SYG_E_BADARG, "%s", err.c_str());
+    for (int i = 0; i < b.nb; ++i) {
+        if (lo) lo[i] = b.lo[i];
+        if (cnt) cnt[i] = b.cnt[i];
+        if (nq) nq[i] = b.nq[i];
+    }
+    return SYG_OK;
+}
+
+int syg_host_alloc(void** p, size_t bytes) {
+    if (!p) return fail(SYG_E_BADARG, "p is NULL");
+    *p = nullptr;
+    CK(cudaHostAlloc(p, std::max<size_t>(bytes, 1), cudaHostAllocDefault));
+    return SYG_OK;
+}
+
+int syg_host_free(void* p) {
+    if (!p) return SYG_OK;
+    CK(cudaFreeHost(p));
+    return SYG_OK;
+}
+
+}  // extern "C"

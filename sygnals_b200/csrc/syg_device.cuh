@@ -1,0 +1,398 @@
+// sygnals_b200/csrc/syg_device.cuh
+//
+// Device building blocks shared by every kernel of the engine:
+//   * in-register radix-2/4/8/16/32 DFT (decimation in frequency, compile-time twiddles),
+//   * the shared-memory Stockham exchange used between register passes,
+//   * CTA / thread-group scans and reductions (FP64 where the reference accumulates in float64),
+//   * warp-level selection (bitonic sort, exact n-th order statistic) for spectral contrast.
+//
+// Tile model: a CTA of kThreads threads owns kThreads*E complex points per "round".  A frame of n_fft real
+// samples is packed into M = n_fft/2 complex points (z[n] = x[2n] + i x[2n+1]); G = M/E threads cooperate on one
+// frame and F = kThreads/G frames are transformed per round, all groups in lock step.
+#pragma once
+
+#include "syg_platform.h"
+
+namespace sygdev {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+// --------------------------------------------------------------------------------------------------------
+// shared-memory access wrappers (bank accounting in the emulator build; plain ld/st in the CUDA build)
+// --------------------------------------------------------------------------------------------------------
+#ifdef SYG_EMU
+template <class T> SYG_INLINE T sld_(const T* p, int site) { ::sygemu::smem_access(p, sizeof(T), site); return *p; }
+template <class T> SYG_INLINE void sst_(T* p, T v, int site) { ::sygemu::smem_access(p, sizeof(T), site); *p = v; }
+#define SLD(p) ::sygdev::sld_((p), __LINE__)
+#define SST(p, v) ::sygdev::sst_((p), (v), __LINE__)
+#else
+#define SLD(p) (*(p))
+#define SST(p, v) (*(p) = (v))
+#endif
+
+// one padding word per 32: makes the stride-E writes of the first Stockham pass conflict free
+SYG_DEVICE SYG_INLINE int padi(int i) { return i + (i >> 5); }
+SYG_HD constexpr int padded_size(int n) { return n + (n >> 5) + 1; }
+
+// --------------------------------------------------------------------------------------------------------
+// compile-time twiddles  W_32^k = exp(-2 pi i k / 32)
+// --------------------------------------------------------------------------------------------------------
+SYG_DEVICE SYG_INLINE constexpr float cos32(int k) {
+    constexpr float c[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                            0.70710678118654752f, 0.55557023301960218f, 0.38268343236508978f,
+                            0.19509032201612825f, 0.0f};
+    k &= 31;
+    if (k > 16) k = 32 - k;           // cos is even
+    return (k <= 8) ? c[k] : -c[16 - k];
+}
+SYG_DEVICE SYG_INLINE constexpr float sin32(int k) { return cos32(k - 8); }  // sin(x) = cos(x - pi/2)
+
+// (xr, xi) *= W_R^K  with K, R compile-time after unrolling; trivial rotations cost no multiplies
+template <int R>
+SYG_DEVICE SYG_INLINE void mul_w(float& xr, float& xi, int k) {
+    k &= (R - 1);
+    const int k32 = k * (32 / R);
+    if (k32 == 0) {
+    } else if (k32 == 8) {            // * (-i)
+        float t = xr; xr = xi; xi = -t;
+    } else if (k32 == 16) {
+        xr = -xr; xi = -xi;
+    } else if (k32 == 24) {           // * (+i)
+        float t = xr; xr = -xi; xi = t;
+    } else if (k32 == 4) {            // (1 - i)/sqrt2
+        float a = xr, b = xi; xr = (a + b) * 0.70710678118654752f; xi = (b - a) * 0.70710678118654752f;
+    } else if (k32 == 12) {           // (-1 - i)/sqrt2
+        float a = xr, b = xi; xr = (b - a) * 0.70710678118654752f; xi = -(a + b) * 0.70710678118654752f;
+    } else if (k32 == 20) {           // (-1 + i)/sqrt2
+        float a = xr, b = xi; xr = -(a + b) * 0.70710678118654752f; xi = (a - b) * 0.70710678118654752f;
+    } else if (k32 == 28) {           // (1 + i)/sqrt2
+        float a = xr, b = xi; xr = (a - b) * 0.70710678118654752f; xi = (a + b) * 0.70710678118654752f;
+    } else {
+        const float c = cos32(k32), s = -sin32(k32);   // W = c + i s
+        float a = xr, b = xi;
+        xr = __fmaf_rn(a, c, -b * s);
+        xi = __fmaf_rn(a, s, b * c);
+    }
+}
+
+SYG_HD constexpr int bitrev(int v, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+SYG_HD constexpr int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// In-register DFT of R points held at xr[o + i*s], xi[o + i*s] (i = 0..R-1): decimation in frequency, in place.
+// Output X[k] ends up at position bitrev(k) (callers index with bitrev at compile time -> free).
+template <int R, int S>
+SYG_DEVICE SYG_INLINE void dft_dif(float* xr, float* xi) {
+    SYG_UNROLL
+    for (int half = R / 2; half >= 1; half >>= 1) {
+        SYG_UNROLL
+        for (int base = 0; base < R; base += 2 * half) {
+            SYG_UNROLL
+            for (int k = 0; k < half; ++k) {
+                const int i0 = (base + k) * S, i1 = (base + k + half) * S;
+                float ar = xr[i0], ai = xi[i0], br = xr[i1], bi = xi[i1];
+                xr[i0] = ar + br; xi[i0] = ai + bi;
+                float dr = ar - br, di = ai - bi;
+                mul_w<R>(dr, di, k * (R / (2 * half)));
+                xr[i1] = dr; xi[i1] = di;
+            }
+        }
+    }
+}
+
+// complex multiply by a run-time twiddle (wr + i wi)
+SYG_DEVICE SYG_INLINE void cmul(float& xr, float& xi, float wr, float wi) {
+    float a = xr, b = xi;
+    xr = __fmaf_rn(a, wr, -b * wi);
+    xi = __fmaf_rn(a, wi, b * wr);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// FFT plan constants for a (LOG2M, E) tile
+// --------------------------------------------------------------------------------------------------------
+template <int LOG2M_, int E_>
+struct FftTile {
+    static constexpr int LOG2M = LOG2M_;
+    static constexpr int E = E_;
+    static constexpr int LOG2E = ilog2(E_);
+    static constexpr int M = 1 << LOG2M_;                 // complex points per frame
+    static constexpr int NFFT = 2 * M;                    // real samples per frame
+    static constexpr int G = M / E_;                      // threads per frame
+    static constexpr int F = kThreads / G;                // frames per round
+    static constexpr int NPASS = (LOG2M_ + LOG2E - 1) / LOG2E;
+    static constexpr int RLAST = 1 << (LOG2M_ - (NPASS - 1) * LOG2E);   // radix of the last pass
+    static constexpr int MP = padded_size(M);             // padded complex stride of one frame in smem
+    static constexpr int PW = padded_size(M + 1);         // padded power-spectrum stride of one frame
+    static_assert(M >= E_, "frame too small for this tile");
+    static_assert(G <= kThreads, "frame too large for this tile");
+};
+
+// One Stockham pass >= 2: gather E points from smem (stride M/R), twiddle, radix-R DFT, scatter back.
+// tw[i] = exp(-2 pi i * i / M).  Two CTA barriers: all gathers complete before any scatter; scatters visible after.
+template <class TL, int R, int NS>
+SYG_DEVICE SYG_INLINE void stockham_pass(float* sre, float* sim, int fbase, int j, const float2* __restrict__ tw) {
+    constexpr int E = TL::E, M = TL::M, G = TL::G, Q = E / R;
+    float xr[E], xi[E];
+    SYG_UNROLL
+    for (int q = 0; q < Q; ++q) {
+        const int b = j + q * G;
+        SYG_UNROLL
+        for (int r = 0; r < R; ++r) {
+            const int idx = fbase + padi(b + r * (M / R));
+            xr[q * R + r] = SLD(&sre[idx]);
+            xi[q * R + r] = SLD(&sim[idx]);
+        }
+    }
+    __syncthreads();
+    SYG_UNROLL
+    for (int q = 0; q < Q; ++q) {
+        const int b = j + q * G;
+        const int k = b & (NS - 1);
+        constexpr int SH = TL::LOG2M - ilog2(NS * R);     // W_{NS*R}^{rk} = W_M^{rk << SH}
+        SYG_UNROLL
+        for (int r = 1; r < R; ++r) {
+            const float2 w = __ldg(&tw[(r * k) << SH]);
+            cmul(xr[q * R + r], xi[q * R + r], w.x, w.y);
+        }
+        dft_dif<R, 1>(xr + q * R, xi + q * R);
+        const int base = fbase, ob = (b - k) * R + k;
+        SYG_UNROLL
+        for (int kp = 0; kp < R; ++kp) {
+            const int src = q * R + bitrev(kp, ilog2(R));
+            const int idx = base + padi(ob + kp * NS);
+            SST(&sre[idx], xr[src]);
+            SST(&sim[idx], xi[src]);
+        }
+    }
+    __syncthreads();
+}
+
+// Full forward FFT of the CTA tile.  On entry xr/xi hold z[j + r*G] (r = 0..E-1) of frame f for each thread;
+// on exit sre/sim[f*MP + padi(k)] hold Z[k] in natural order (after a CTA barrier).
+template <class TL>
+SYG_DEVICE SYG_INLINE void fft_tile_forward(float (&xr)[TL::E], float (&xi)[TL::E], float* sre, float* sim, int f, int j,
+                                          const float2* __restrict__ tw) {
+    constexpr int E = TL::E, LE = TL::LOG2E;
+    const int fbase = f * TL::MP;
+    // pass 1: radix E, NS = 1, no twiddles; thread j owns butterfly j and scatters to j*E + k'
+    dft_dif<E, 1>(xr, xi);
+    SYG_UNROLL
+    for (int kp = 0; kp < E; ++kp) {
+        const int idx = fbase + padi(j * E + kp);
+        SST(&sre[idx], xr[bitrev(kp, LE)]);
+        SST(&sim[idx], xi[bitrev(kp, LE)]);
+    }
+    __syncthreads();
+    if constexpr (TL::NPASS >= 2) {
+        if constexpr (TL::NPASS == 2) stockham_pass<TL, TL::RLAST, E>(sre, sim, fbase, j, tw);
+        else stockham_pass<TL, E, E>(sre, sim, fbase, j, tw);
+    }
+    if constexpr (TL::NPASS >= 3) {
+        if constexpr (TL::NPASS == 3) stockham_pass<TL, TL::RLAST, E * E>(sre, sim, fbase, j, tw);
+        else stockham_pass<TL, E, E * E>(sre, sim, fbase, j, tw);
+    }
+    static_assert(TL::NPASS <= 3, "tile supports at most three passes");
+}
+
+// Real-input split for bin k (0 <= k <= M/2): given Z[k], Z[M-k] and Wk = exp(-2 pi i k / N) produce X[k], X[M-k].
+SYG_DEVICE SYG_INLINE void real_split(float zkr, float zki, float zmr, float zmi, float wr, float wi,
+                                    float& xkr, float& xki, float& xmr, float& xmi) {
+    const float ar = 0.5f * (zkr + zmr), ai = 0.5f * (zki - zmi);     // A = (Zk + conj Zm)/2
+    const float br = 0.5f * (zkr - zmr), bi = 0.5f * (zki + zmi);     // B = (Zk - conj Zm)/2
+    const float cr = __fmaf_rn(br, wr, -bi * wi), ci = __fmaf_rn(br, wi, bi * wr);   // C = W^k B
+    xkr = ar + ci; xki = ai - cr;                                     // X[k]   = A - i C
+    xmr = ar - ci; xmi = -(ai + cr);                                  // X[M-k] = conj(A + i C)
+}
+
+// --------------------------------------------------------------------------------------------------------
+// thread-group collectives.  Groups are G consecutive threads (G a power of two, 1..kThreads); every thread of
+// the CTA calls them (lock step).  scratch: kThreads/32 doubles of shared memory.
+// --------------------------------------------------------------------------------------------------------
+template <int G>
+SYG_DEVICE SYG_INLINE double group_sum(double v, double* scratch) {
+    constexpr int W = G < 32 ? G : 32;
+    SYG_UNROLL
+    for (int o = W / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o, W);
+    if constexpr (G > 32) {
+        const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+        __syncthreads();
+        if (lane == 0) scratch[warp] = v;
+        __syncthreads();
+        constexpr int WG = G / 32;
+        const int w0 = (warp / WG) * WG;
+        double t = 0.0;
+        SYG_UNROLL
+        for (int i = 0; i < WG; ++i) t += scratch[w0 + i];
+        v = t;
+    }
+    return v;
+}
+
+template <int G>
+SYG_DEVICE SYG_INLINE float group_max(float v, double* scratch) {
+    constexpr int W = G < 32 ? G : 32;
+    SYG_UNROLL
+    for (int o = W / 2; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o, W));
+    if constexpr (G > 32) {
+        const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+        float* fs = reinterpret_cast<float*>(scratch);
+        __syncthreads();
+        if (lane == 0) fs[warp] = v;
+        __syncthreads();
+        constexpr int WG = G / 32;
+        const int w0 = (warp / WG) * WG;
+        float t = fs[w0];
+        SYG_UNROLL
+        for (int i = 1; i < WG; ++i) t = fmaxf(t, fs[w0 + i]);
+        v = t;
+    }
+    return v;
+}
+
+// inclusive scan over the group (thread order); returns this thread's inclusive prefix
+template <int G>
+SYG_DEVICE SYG_INLINE double group_scan_incl(double v, double* scratch) {
+    constexpr int W = G < 32 ? G : 32;
+    const int tid = threadIdx.x, lane = tid & 31, gl = lane & (W - 1);
+    SYG_UNROLL
+    for (int o = 1; o < W; o <<= 1) {
+        double n = __shfl_up_sync(kFull, v, o, W);
+        if (gl >= o) v += n;
+    }
+    if constexpr (G > 32) {
+        const int warp = tid >> 5;
+        __syncthreads();
+        if (lane == 31) scratch[warp] = v;
+        __syncthreads();
+        constexpr int WG = G / 32;
+        const int w0 = (warp / WG) * WG;
+        double pre = 0.0;
+        for (int i = w0; i < warp; ++i) pre += scratch[i];
+        v += pre;
+    }
+    return v;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// warp-level selection
+// --------------------------------------------------------------------------------------------------------
+// full-warp bitonic sort, descending by lane (lane 0 gets the largest)
+SYG_DEVICE SYG_INLINE float warp_sort_desc(float v) {
+    const int lane = threadIdx.x & 31;
+    SYG_UNROLL
+    for (int k = 2; k <= 32; k <<= 1) {
+        SYG_UNROLL
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            const float o = __shfl_xor_sync(kFull, v, jj);
+            const bool desc = ((lane & k) == 0);          // block direction (k == 32: descending everywhere)
+            const bool lower = ((lane & jj) == 0);
+            v = (lower == desc) ? fmaxf(v, o) : fminf(v, o);
+        }
+    }
+    return v;
+}
+
+SYG_DEVICE SYG_INLINE float warp_sum(float v) {
+    SYG_UNROLL
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+SYG_DEVICE SYG_INLINE float warp_max(float v) {
+    SYG_UNROLL
+    for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+SYG_DEVICE SYG_INLINE int warp_excl_scan(int v, int& total) {
+    const int lane = threadIdx.x & 31;
+    int x = v;
+    SYG_UNROLL
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(kFull, x, o);
+        if (lane >= o) x += n;
+    }
+    total = __shfl_sync(kFull, x, 31);
+    return x - v;
+}
+
+// Mean of sqrt() of the n largest (SIGN=+1) or n smallest (SIGN=-1) of the `count` non-negative values
+// p[padi(lo + i)], i < count, taken by one full warp.  Selection is exact (ties irrelevant: only values
+// enter the mean).  cand: 32 floats of warp-private shared memory.
+template <int SIGN>
+SYG_DEVICE SYG_INLINE float warp_extreme_mean_sqrt(const float* p, int lo, int count, int n, float* cand) {
+    const int lane = threadIdx.x & 31;
+    if (count <= 0) return __uint_as_float(0x7fc00000u);   // mean of nothing -> NaN (numpy)
+    if (n > count) n = count;
+    const float NEG = -3.0e38f;
+    // key(x) = SIGN * x : "largest key" selection in both directions
+    float lmax = NEG;
+    int have = 0;
+    for (int i = lane; i < count; i += 32) {
+        const float key = SIGN * SLD(&p[padi(lo + i)]);
+        lmax = fmaxf(lmax, key);
+        have = 1;
+    }
+    (void)have;
+    float thr = NEG;
+    bool fast = (n <= 32);
+    if (fast && count > 32) {
+        const float srt = warp_sort_desc(lmax);
+        thr = __shfl_sync(kFull, srt, n - 1);              // >= n values are >= thr
+    }
+    int c_total = count;
+    if (fast) {
+        int cnt = 0;
+        if (count > 32) {
+            for (int i = lane; i < count; i += 32) cnt += (SIGN * SLD(&p[padi(lo + i)]) >= thr) ? 1 : 0;
+        } else {
+            cnt = (lane < count) ? 1 : 0;
+        }
+        const int base = warp_excl_scan(cnt, c_total);
+        if (c_total <= 32) {
+            int slot = base;
+            for (int i = lane; i < count; i += 32) {
+                const float key = SIGN * SLD(&p[padi(lo + i)]);
+                if (key >= thr) cand[slot++] = key;
+            }
+            __syncwarp();
+            float v = (lane < c_total) ? cand[lane] : NEG;
+            __syncwarp();
+            v = warp_sort_desc(v);
+            const float contrib = (lane < n) ? sqrtf(SIGN * v) : 0.0f;
+            return warp_sum(contrib) / (float)n;
+        }
+    }
+    // exact slow path (n > 32 or many ties): bitwise search for the n-th largest key, on an order-preserving
+    // unsigned image of the float key
+    auto okey = [](float k) -> unsigned {
+        unsigned u = __float_as_uint(k);
+        return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    };
+    unsigned prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned trial = prefix | (1u << bit);
+        int cnt = 0;
+        for (int i = lane; i < count; i += 32) cnt += (okey(SIGN * SLD(&p[padi(lo + i)])) >= trial) ? 1 : 0;
+        cnt = __reduce_add_sync(kFull, cnt);
+        if (cnt >= n) prefix = trial;
+    }
+    // prefix == okey(n-th largest key)
+    float s_gt = 0.0f;
+    int c_gt = 0;
+    float tval = 0.0f;
+    for (int i = lane; i < count; i += 32) {
+        const float key = SIGN * SLD(&p[padi(lo + i)]);
+        const unsigned ok = okey(key);
+        if (ok > prefix) { s_gt += sqrtf(SIGN * key); c_gt++; }
+        if (ok == prefix) tval = SIGN * key;
+    }
+    s_gt = warp_sum(s_gt);
+    c_gt = __reduce_add_sync(kFull, c_gt);
+    tval = warp_max(tval);                                  // all lanes holding it agree; others contribute 0 (values >= 0)
+    return (s_gt + (float)(n - c_gt) * sqrtf(tval)) / (float)n;
+}
+
+}  // namespace sygdev

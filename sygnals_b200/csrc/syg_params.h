@@ -1,0 +1,97 @@
+// sygnals_b200/csrc/syg_params.h -- kernel argument blocks (host fills, device reads; passed by value).
+#pragma once
+
+#include "syg_platform.h"
+
+namespace syg {
+
+// feature bits (kernel-internal; the public ids live in include/sygb200.h)
+enum : unsigned {
+    FB_MFCC = 1u << 0, FB_CONTRAST = 1u << 1, FB_CENTROID = 1u << 2, FB_ROLLOFF = 1u << 3, FB_RMS = 1u << 4,
+    FB_CREST = 1u << 5, FB_PEAK = 1u << 6, FB_BANDWIDTH = 1u << 7, FB_FLATNESS = 1u << 8, FB_DOMINANT = 1u << 9,
+    FB_ZCR = 1u << 10, FB_MEAN_AMP = 1u << 11, FB_STD_AMP = 1u << 12,
+};
+constexpr unsigned FB_SPECTRUM_ANY = FB_MFCC | FB_CONTRAST | FB_CENTROID | FB_ROLLOFF | FB_BANDWIDTH | FB_FLATNESS | FB_DOMINANT;
+constexpr unsigned FB_SPECSTATS = FB_CENTROID | FB_ROLLOFF | FB_BANDWIDTH | FB_FLATNESS | FB_DOMINANT;
+constexpr unsigned FB_TIME_ANY = FB_RMS | FB_CREST | FB_PEAK | FB_ZCR | FB_MEAN_AMP | FB_STD_AMP;
+
+constexpr int kMaxBands = 12;   // spectral-contrast bands incl. the top one (n_bands + 1)
+
+struct UnitGeom {
+    long long n_units;          // units handled by this launch
+    long long unit_len;         // padded length of a unit (samples)
+    long long unit_stride;      // start_u = u * unit_stride                (if unit_starts == nullptr)
+    long long total_len;        // samples in y; valid_u = clamp(total_len - start_u, 0, unit_len)
+    const long long* unit_starts;   // optional [n_units] (device)
+    const int* unit_valid;          // optional [n_units] (device)
+    long long unit0;            // first unit of this launch in the caller's numbering (analytic starts only;
+                                // unit_starts / unit_valid are passed already offset)
+};
+
+struct FrameArgs {
+    const float* y;
+    UnitGeom g;
+    int T;                      // frames per unit
+    int hop;
+    int cpad;                   // n_fft/2 when centred, else 0
+    int pad_mode;               // 0 constant (zeros), 1 reflect
+    long long n_frames;         // g.n_units * T
+    const float* window;        // [n_fft], already zero-padded/centred to n_fft
+    const float2* tw;           // [M]      exp(-2 pi i k / M)
+    const float2* tws;          // [M/2+1]  exp(-2 pi i k / n_fft)
+    // ---- features
+    unsigned mask;
+    double bin_hz;              // frequency of bin 1 (numpy rfftfreq step)
+    double roll_percent;
+    int n_mels;
+    const int* mel_start;       // [n_mels] first bin with non-zero weight
+    const int* mel_len;         // [n_mels]
+    const int* mel_off;         // [n_mels] offset into mel_w
+    const float* mel_w;
+    int mel_power_is_2;
+    float mel_half_power;       // power / 2 (applied to |X|^2)
+    int nb;                     // contrast bands incl. top (0 = off)
+    int band_lo[kMaxBands];     // first bin
+    int band_cnt[kMaxBands];    // bins in the (already "drop last row"-ed) sub-band
+    int band_n[kMaxBands];      // quantile count
+    // per-frame rows written directly (row < 0: not requested)
+    int row_centroid, row_rolloff, row_rms, row_crest, row_peak, row_bandwidth, row_flatness, row_dominant,
+        row_zcr, row_mean_amp, row_std_amp;
+    int n_rows;
+    float* out;                 // [n_units][n_rows][T]
+    float* melws;               // [n_frames][n_mels]   raw mel energies
+    float* cws;                 // [n_frames][2*nb]     contrast peaks | valleys (linear)
+    unsigned* unit_max;         // [n_units][4]         bit images of max mel energy, max peak, max valley
+    // ---- stft
+    int out_kind;               // 0 complex64, 1 magnitude, 2 power
+    void* stft_out;             // [n_units][B][T]
+};
+
+struct FinalizeArgs {
+    long long n_units;
+    int T, n_rows;
+    int n_mels, n_mfcc, row_mfcc;       // row_mfcc < 0: no mfcc
+    const float* dct;                   // [n_mfcc][n_mels] (lifter folded in)
+    int nb, row_contrast;               // nb == 0: no contrast
+    float amin, top_db;
+    const float* melws;
+    const float* cws;
+    const unsigned* unit_max;
+    float* out;
+};
+
+struct WelchArgs {
+    const float* y;
+    UnitGeom g;
+    int nperseg, step, nseg;    // sub-segment length (<= nfft), hop, count per unit
+    int detrend;                // 1: subtract sub-segment mean
+    const float* window;        // [nfft] (nperseg window values then zeros)
+    const float2* tw;
+    const float2* tws;
+    float scale;                // 1/(fs*sum w^2) or 1/(sum w)^2
+    int onesided_double;        // 1: double all bins except DC (and Nyquist for even nfft)
+    float* psd;                 // [n_units][B]
+    float* stats;               // optional [n_units][3]: rms, crest, peak over the unit's unit_len samples
+};
+
+}  // namespace syg

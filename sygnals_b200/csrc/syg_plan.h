@@ -1,0 +1,221 @@
+// sygnals_b200/csrc/syg_plan.h -- host-side construction of the constant tables (double precision, rounded once).
+//
+// Each builder follows the routine the reference calls (librosa / scipy semantics):
+//   window      scipy.signal.get_window(name, win_length, fftbins=True) + librosa.util.pad_center   (A.1)
+//   mel basis   librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney', float32) (A.3)
+//   dct         scipy.fftpack.dct(type, norm)[:n_mfcc] + librosa lifter                              (A.6)
+//   bands       librosa.feature.spectral_contrast octave-band membership and quantile counts         (A.7)
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace sygplan {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+inline bool build_window(int window, int win_length, int n_fft, std::vector<float>& out, std::string& err) {
+    if (win_length < 1 || win_length > n_fft) { err = "win_length must be in [1, n_fft]"; return false; }
+    double a[3] = {0, 0, 0};
+    int na = 0;
+    switch (window) {
+        case 0: a[0] = 0.5; a[1] = 0.5; na = 2; break;                 // hann
+        case 1: a[0] = 0.54; a[1] = 0.46; na = 2; break;               // hamming
+        case 2: a[0] = 0.42; a[1] = 0.5; a[2] = 0.08; na = 3; break;   // blackman
+        case 3: a[0] = 1.0; na = 1; break;                             // boxcar
+        default: err = "unsupported window id"; return false;
+    }
+    out.assign(n_fft, 0.0f);
+    const int lpad = (n_fft - win_length) / 2;                         // librosa.util.pad_center
+    for (int n = 0; n < win_length; ++n) {
+        double w = a[0];
+        double sgn = -1.0;
+        for (int i = 1; i < na; ++i) { w += sgn * a[i] * std::cos(2.0 * kPi * i * n / (double)win_length); sgn = -sgn; }
+        out[lpad + n] = (float)w;
+    }
+    return true;
+}
+
+inline double window_value_d(int window, int win_length, int n) {
+    double a[3] = {0, 0, 0};
+    int na = 0;
+    switch (window) {
+        case 0: a[0] = 0.5; a[1] = 0.5; na = 2; break;
+        case 1: a[0] = 0.54; a[1] = 0.46; na = 2; break;
+        case 2: a[0] = 0.42; a[1] = 0.5; a[2] = 0.08; na = 3; break;
+        default: a[0] = 1.0; na = 1; break;
+    }
+    double w = a[0], sgn = -1.0;
+    for (int i = 1; i < na; ++i) { w += sgn * a[i] * std::cos(2.0 * kPi * i * n / (double)win_length); sgn = -sgn; }
+    return w;
+}
+
+// numpy.fft.rfftfreq(n_fft, 1/sr) step, with numpy's operation order
+inline double bin_hz(double sr, int n_fft) {
+    const double d = 1.0 / sr;
+    return 1.0 / ((double)n_fft * d);
+}
+
+inline double hz_to_mel(double f) {                       // Slaney (htk=False)
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    if (f >= min_log_hz) return min_log_mel + std::log(f / min_log_hz) / logstep;
+    return f / f_sp;
+}
+inline double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    if (m >= min_log_mel) return min_log_hz * std::exp(logstep * (m - min_log_mel));
+    return f_sp * m;
+}
+
+struct MelTable {
+    int n_mels = 0, n_bins = 0;
+    std::vector<int> start, len, off;
+    std::vector<float> w;            // concatenated non-zero spans
+    std::vector<float> dense;        // optional [n_mels][n_bins]
+};
+
+inline bool build_mel(double sr, int n_fft, int n_mels, double fmin, double fmax, bool want_dense, MelTable& t,
+                      std::string& err) {
+    if (n_mels < 1) { err = "n_mels must be >= 1"; return false; }
+    if (fmax <= 0) fmax = sr / 2.0;
+    const int B = 1 + n_fft / 2;
+    t.n_mels = n_mels; t.n_bins = B;
+    t.start.assign(n_mels, 0); t.len.assign(n_mels, 0); t.off.assign(n_mels, 0);
+    t.w.clear();
+    if (want_dense) t.dense.assign((size_t)n_mels * B, 0.0f);
+    const double step_hz = bin_hz(sr, n_fft);
+    // mel_frequencies(n_mels + 2): np.linspace(min_mel, max_mel, n) then mel_to_hz
+    const int n = n_mels + 2;
+    const double mn = hz_to_mel(fmin), mx = hz_to_mel(fmax);
+    std::vector<double> mel_f(n);
+    const double lstep = (mx - mn) / (double)(n - 1);
+    for (int i = 0; i < n; ++i) mel_f[i] = mel_to_hz(i == n - 1 ? mx : mn + lstep * (double)i);
+    std::vector<float> row(B);
+    for (int i = 0; i < n_mels; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        int first = -1, last = -1;
+        for (int k = 0; k < B; ++k) {
+            const double fk = (double)k * step_hz;
+            const double lower = -(mel_f[i] - fk) / fd0;
+            const double upper = (mel_f[i + 2] - fk) / fd1;
+            double v = lower < upper ? lower : upper;
+            if (!(v > 0.0)) v = 0.0;
+            float wf = (float)v;                          // weights stored as float32 ...
+            wf = (float)((double)wf * enorm);             // ... then `weights *= enorm` (float32 result)
+            row[k] = wf;
+            if (wf != 0.0f) { if (first < 0) first = k; last = k; }
+        }
+        t.off[i] = (int)t.w.size();
+        if (first >= 0) {
+            t.start[i] = first; t.len[i] = last - first + 1;
+            for (int k = first; k <= last; ++k) t.w.push_back(row[k]);
+        }
+        if (want_dense) for (int k = 0; k < B; ++k) t.dense[(size_t)i * B + k] = row[k];
+    }
+    if (t.w.empty()) t.w.push_back(0.0f);
+    return true;
+}
+
+// rows [n_out][n_mels] of the DCT scipy.fftpack.dct(x, type, norm) restricted to the first n_out outputs,
+// with librosa's sinusoidal lifter folded in.
+inline bool build_dct(int n_out, int N, int type, bool ortho, double lifter, int n_mfcc_for_lifter,
+                      std::vector<float>& out, std::string& err) {
+    if (n_out < 1 || n_out > N) { err = "n_mfcc must be in [1, n_mels]"; return false; }
+    if (lifter < 0) { err = "MFCC lifter must be a non-negative number"; return false; }
+    out.assign((size_t)n_out * N, 0.0f);
+    for (int k = 0; k < n_out; ++k) {
+        double lift = 1.0;
+        if (lifter > 0) lift = 1.0 + (lifter / 2.0) * std::sin(kPi * (double)(k + 1) / lifter);
+        (void)n_mfcc_for_lifter;
+        for (int n = 0; n < N; ++n) {
+            double v;
+            if (type == 2) {
+                v = 2.0 * std::cos(kPi * (double)k * (2.0 * n + 1.0) / (2.0 * N));
+                if (ortho) v *= (k == 0) ? std::sqrt(1.0 / (4.0 * N)) : std::sqrt(1.0 / (2.0 * N));
+            } else if (type == 3) {
+                if (ortho) v = (n == 0) ? 1.0 / std::sqrt((double)N)
+                                        : std::sqrt(2.0 / N) * std::cos(kPi * (2.0 * k + 1.0) * n / (2.0 * N));
+                else v = (n == 0) ? 1.0 : 2.0 * std::cos(kPi * (2.0 * k + 1.0) * n / (2.0 * N));
+            } else if (type == 1 && !ortho && N >= 2) {
+                if (n == 0) v = 1.0;
+                else if (n == N - 1) v = (k % 2 == 0) ? 1.0 : -1.0;
+                else v = 2.0 * std::cos(kPi * (double)k * n / (double)(N - 1));
+            } else {
+                err = "unsupported dct_type/norm combination";
+                return false;
+            }
+            out[(size_t)k * N + n] = (float)(v * lift);
+        }
+    }
+    return true;
+}
+
+struct Bands { int nb = 0; int lo[16]; int cnt[16]; int nq[16]; };
+
+inline bool build_bands(double sr, int n_fft, int n_bands, double fmin, double quantile, Bands& b, std::string& err) {
+    if (n_bands < 1 || n_bands + 1 > 12) { err = "n_bands must be in [1, 11]"; return false; }
+    if (!(quantile > 0.0 && quantile < 1.0)) { err = "quantile must lie in the range (0, 1)"; return false; }
+    if (!(fmin > 0)) { err = "fmin must be a positive number"; return false; }
+    const int B = 1 + n_fft / 2;
+    const double step = bin_hz(sr, n_fft);
+    std::vector<double> octa(n_bands + 2, 0.0);
+    for (int i = 1; i < n_bands + 2; ++i) octa[i] = fmin * std::pow(2.0, (double)(i - 1));
+    for (int i = 0; i < n_bands + 1; ++i)
+        if (octa[i] >= 0.5 * sr) { err = "Frequency band exceeds Nyquist. Reduce either fmin or n_bands."; return false; }
+    b.nb = n_bands + 1;
+    for (int k = 0; k <= n_bands; ++k) {
+        const double lo = octa[k], hi = octa[k + 1];
+        int first = -1, last = -1;
+        for (int i = 0; i < B; ++i) {
+            const double f = (double)i * step;
+            if (f >= lo && f <= hi) { if (first < 0) first = i; last = i; }
+        }
+        if (first < 0) { err = "spectral_contrast band without FFT bins"; return false; }
+        if (k > 0) first = (first > 0) ? first - 1 : first;
+        if (k == n_bands) last = B - 1;
+        const int total = last - first + 1;
+        const int rows = total - (k < n_bands ? 1 : 0);
+        double q = std::nearbyint(quantile * (double)total);      // np.rint (half to even)
+        int nq = (int)(q < 1.0 ? 1.0 : q);
+        b.lo[k] = first; b.cnt[k] = rows; b.nq[k] = nq;
+    }
+    return true;
+}
+
+// segment_fixed_length boundary arithmetic (segmentation.py:62-114)
+inline int64_t segment_table(int64_t total, double sr, double sec, double ovl, bool pad, double min_sec,
+                             int64_t* seg_len, int64_t* seg_hop, int64_t* starts, int32_t* valid, int64_t cap,
+                             std::string& err) {
+    if (!(sec > 0)) { err = "segment_length_sec must be positive."; return -1; }
+    if (!(ovl >= 0.0 && ovl < 1.0)) { err = "overlap_ratio must be between 0.0 and < 1.0."; return -1; }
+    const int64_t seg = (int64_t)(sec * sr);                    // int() truncation (:62)
+    if (seg_len) *seg_len = seg;
+    if (seg == 0) { if (seg_hop) *seg_hop = 0; return 0; }
+    int64_t hop = (int64_t)((double)seg * (1.0 - ovl));         // :67
+    if (hop < 1) hop = 1;
+    if (seg_hop) *seg_hop = hop;
+    const int64_t min_samples = (min_sec >= 0) ? (int64_t)(min_sec * sr) : 0;   // :71
+    int64_t n = 0;
+    for (int64_t start = 0; start < total; start += hop) {
+        const int64_t end = start + seg;
+        const int64_t orig = (end < total ? end : total) - start;
+        bool keep = false;
+        if (min_samples > 0 && orig < min_samples) keep = false;
+        else if (end > total) keep = pad;
+        else keep = true;
+        if (keep) {
+            if (starts && n < cap) starts[n] = start;
+            if (valid && n < cap) valid[n] = (int32_t)orig;
+            ++n;
+        }
+        if (!pad && start + hop + seg > total) break;            // :113-114
+    }
+    return n;
+}
+
+}  // namespace sygplan

@@ -1,0 +1,278 @@
+"""Parity of the CUDA kernels (called through the C ABI, include/sygb200.h) against
+
+* the committed golden vectors produced by the UNMODIFIED reference (tests/golden/make_golden.py), and
+* the oracle (oracle/sygnals_oracle.py) on seeded inputs, incl. the edge cases the reference's tests cover.
+
+Every test runs twice: on the B200 (``gpu`` marker, the product library) and -- the same kernel sources compiled
+for the CPU fiber emulator (tests/emu, test infrastructure only) -- in the GPU-less container.
+
+Tolerances (SURVEY.md section 8(a) note; the engine computes in FP32, the reference in float64):
+  frame counts / boundaries / shapes                      exact
+  power            |dP| <= 1e-4 * P + 1e-6 * max_bin(P) per frame
+  MFCC             abs 1e-3
+  centroid         rel 1e-5 + 1e-6 * Nyquist (the FP32 noise floor of empty bins is weighted by their frequency)
+  rms / crest      rel 1e-5
+  rolloff          exact on >= 99.9 % of frames, never more than one bin off
+  contrast (dB)    abs 1e-3 dB on >= 99 % of entries, abs 2e-2 dB everywhere: the valley of a band is its smallest
+                   magnitude, whose FP32 FFT error is relative to the frame's LARGEST bin, so deep
+                   nulls cannot meet 1e-3 dB in FP32.
+"""
+import numpy as np
+import pytest
+
+import cases
+from backends import BACKENDS, get_engine
+from oracle import sygnals_oracle as orc
+from sygnals_b200 import _ffi
+from sygnals_b200.utils import synth
+
+
+@pytest.fixture(params=BACKENDS)
+def eng(request):
+    return get_engine(request.param)
+
+
+def power_close(P, Pref):
+    """P, Pref: [..., B, T]"""
+    tol = 1e-4 * Pref + 1e-6 * Pref.max(axis=-2, keepdims=True)
+    bad = np.abs(P - Pref) > tol
+    assert not bad.any(), f"{bad.sum()} power bins out of tolerance, worst excess {(np.abs(P - Pref) - tol).max():.3e}"
+
+
+def check_rows(names, got, ref, bin_hz=None, nyq=None, contrast_ok=None):
+    """got/ref: [rows, T] (or [units, rows, T]) in the order of ``names``."""
+    if nyq is None and bin_hz is not None:
+        nyq = 24000.0
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape
+    if got.ndim == 2:
+        got, ref = got[None], ref[None]
+    contrast_d = []
+    for i, n in enumerate(names):
+        g, r = got[:, i], ref[:, i]
+        d = np.abs(g - r)
+        if n.startswith("mfcc_"):
+            assert d.max() <= 1e-3, f"{n}: max abs err {d.max():.3e}"
+        elif n.startswith("contrast_"):
+            assert np.isfinite(g).all()
+            if contrast_ok is not None:
+                d = d[..., contrast_ok]
+            if d.size:
+                assert d.max() <= 2e-2, f"{n}: max abs err {d.max():.3e} dB"
+            contrast_d.append(d.ravel())
+        elif n == "spectral_centroid":
+            assert bin_hz is not None
+            assert (d <= 1e-5 * np.abs(r) + 1e-6 * nyq).all(), f"{n}: worst {d.max():.3e}"
+        elif n in ("rms_energy", "crest_factor", "peak_amplitude", "mean_amplitude", "std_dev_amplitude"):
+            assert (d <= 1e-5 * np.abs(r) + 1e-9).all(), f"{n}: worst rel {(d / (np.abs(r) + 1e-30)).max():.3e}"
+        elif n in ("spectral_rolloff", "dominant_frequency"):
+            assert bin_hz is not None
+            off = d / bin_hz
+            assert off.max() <= 1.0 + 1e-6, f"{n}: off by {off.max():.2f} bins"
+            assert (off > 0.5).mean() <= 1e-3, f"{n}: {(off > 0.5).sum()} of {off.size} frames differ"
+        elif n == "spectral_bandwidth":
+            assert (d <= 1e-4 * np.abs(r) + 1e-2).all(), f"{n}: worst {d.max():.3e}"
+        elif n == "spectral_flatness":
+            assert (d <= 1e-4 * np.abs(r) + 1e-7).all(), f"{n}: worst {d.max():.3e}"
+        else:
+            raise AssertionError(f"no tolerance defined for {n}")
+    if contrast_d and sum(c.size for c in contrast_d):
+        allc = np.concatenate(contrast_d)
+        assert (allc > 1e-3).mean() <= 0.01, f"{(allc > 1e-3).sum()} of {allc.size} contrast entries above 1e-3 dB"
+
+
+def oracle_rows(y, sr, features, fl, hop, feature_params=None, center=True):
+    r = orc.extract_features(np.asarray(y, dtype=np.float64), sr, list(features), frame_length=fl, hop_length=hop,
+                             center=center, feature_params=feature_params)
+    names = [k for k in r if k != "time"]
+    return names, (np.stack([r[k] for k in names]) if names else np.zeros((0, len(r["time"]))))
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+def test_golden_cfg1_mfcc_rms(eng):
+    y, sr = cases.cfg1_input()
+    g = cases.load("cfg1_mfcc_rms.npz")
+    np.testing.assert_allclose(cases.checksum(y), g["in_checksum"], rtol=1e-12)
+    p = _ffi.make_params(eng.lib, sr, ["mfcc", "rms_energy"], 2048, 512, feature_params={"mfcc": {"n_mels": 128, "n_mfcc": 20}})
+    out = eng.features_host(y, eng.units_clips(1, len(y)), p)
+    assert out.shape == (1, 21, 431) and out.dtype == np.float32
+    check_rows([str(n) for n in g["names"]], out[0], g["rows"])
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024, 2048, 4096, 8192])
+def test_golden_cfg2_stft(eng, n_fft):
+    y, sr = cases.cfg2_input()
+    g = cases.load("cfg2_stft_sweep.npz")
+    u = eng.units_clips(y.shape[0], y.shape[1])
+    D = eng.stft_host(y.ravel(), u, n_fft, n_fft // 4, n_fft)
+    mag = eng.stft_host(y.ravel(), u, n_fft, n_fft // 4, n_fft, out_kind=_ffi.OUT_MAGNITUDE)
+    pw = eng.stft_host(y.ravel(), u, n_fft, n_fft // 4, n_fft, out_kind=_ffi.OUT_POWER)
+    for c in range(y.shape[0]):
+        ref = g[f"D_{n_fft}_{c}"].astype(np.complex128)
+        assert D[c].shape == ref.shape == (1 + n_fft // 2, 1 + y.shape[1] // (n_fft // 4))
+        scale = np.abs(ref).max(axis=0, keepdims=True)
+        assert (np.abs(D[c] - ref) <= 2e-6 * scale + 1e-12).all()
+        power_close(pw[c].astype(np.float64), np.abs(ref) ** 2)
+        power_close(mag[c].astype(np.float64) ** 2, np.abs(ref) ** 2)
+
+
+def test_golden_cfg2_reflect_and_nocenter(eng):
+    y, sr = cases.cfg2_input()
+    g = cases.load("cfg2_stft_sweep.npz")
+    u = eng.units_clips(1, y.shape[1])
+    D = eng.stft_host(y[0], u, 1024, 200, 800, pad_mode=_ffi.PAD_IDS["reflect"])
+    ref = g["D_reflect_1024_800_200"]
+    assert D[0].shape == ref.shape
+    assert np.abs(D[0] - ref).max() <= 2e-6 * np.abs(ref).max()
+    D = eng.stft_host(y[0], u, 512, 128, 512, center=False)
+    ref = g["D_nocenter_512_128"]
+    assert D[0].shape == ref.shape
+    assert np.abs(D[0] - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_golden_cfg3_speech_mfcc(eng):
+    y, sr = cases.cfg3_input()
+    g = cases.load("cfg3_speech_mfcc.npz")
+    p = _ffi.make_params(eng.lib, sr, ["mfcc"], 512, 160, feature_params={"mfcc": {"n_mels": 40}})
+    out = eng.features_host(y.ravel(), eng.units_clips(y.shape[0], y.shape[1]), p)
+    assert out.shape == g["rows"].shape == (10, 13, 101)
+    check_rows([str(n) for n in g["names"]], out, g["rows"])
+
+
+def test_golden_cfg4_env_sound(eng):
+    y, sr = cases.cfg4_input()
+    g = cases.load("cfg4_env_sound.npz")
+    seg_len, seg_hop, starts, valid = eng.lib.segment_table(len(y), sr, 2.0, 0.5, True, None)
+    assert (seg_len, seg_hop, len(starts)) == (int(g["seg_len"]), 44100, int(g["n_segments"]))
+    p = _ffi.make_params(eng.lib, sr, cases.CFG4_FEATURES, 2048, 512)
+    out = eng.features_host(y, eng.units_clips(len(starts), seg_len, total_len=len(y), stride=seg_hop), p)
+    assert out.shape == g["rows"].shape == (8, 24, 173)
+    check_rows([str(n) for n in g["names"]], out, g["rows"], bin_hz=sr / 2048)
+    # explicit segment table == analytic geometry, bit for bit
+    out2 = eng.features_host(y, eng.units_table(starts.ctypes.data, valid.ctypes.data, len(starts), seg_len, len(y)), p)
+    assert np.array_equal(out, out2)
+
+
+def test_golden_cfg5_welch(eng):
+    y, sr = cases.cfg5_input()
+    g = cases.load("cfg5_machinery_psd.npz")
+    u = eng.units_clips(6, sr)
+    psd, st = eng.psd_welch_host(y.ravel(), u, sr, 0, 1024, 512, 1024, True, 0, stats=True)
+    ref = g["psd"]
+    assert psd.shape == ref.shape == (6, 513)
+    assert (np.abs(psd - ref) <= 1e-4 * ref + 1e-6 * ref.max(axis=1, keepdims=True)).all()
+    np.testing.assert_allclose(st[:, 0], g["rms"], rtol=1e-5)
+    np.testing.assert_allclose(st[:, 1], g["crest"], rtol=1e-5)
+    pp = eng.psd_welch_host(y[0, :4096], eng.units_clips(1, 4096), sr, 0, 4096, 0, 8192, True, 0)
+    ref = g["periodogram_8192"]
+    assert (np.abs(pp[0] - ref) <= 1e-4 * ref + 1e-6 * ref.max()).all()
+    pp = eng.psd_welch_host(y[1, :sr], eng.units_clips(1, sr), sr, 0, 2048, 1024, 2048, True, 1)
+    ref = g["welch_2048_spectrum"]
+    assert (np.abs(pp[0] - ref) <= 1e-4 * ref + 1e-6 * ref.max()).all()
+
+
+# ------------------------------------------------------------------------------------------------ oracle, seeded
+@pytest.mark.parametrize("sr,fl,hop,n,features,fp", [
+    (16000, 512, 160, 16000, ["mfcc", "spectral_centroid", "spectral_rolloff", "rms_energy", "crest_factor"], {"mfcc": {"n_mels": 40}}),
+    (22050, 1024, 256, 5000, ["spectral_contrast", "mfcc", "peak_amplitude", "spectral_centroid", "spectral_bandwidth", "spectral_flatness",
+                              "dominant_frequency", "mean_amplitude", "std_dev_amplitude"], {"mfcc": {"n_mels": 64, "n_mfcc": 20, "lifter": 22.0}}),
+    (44100, 2048, 512, 9000, ["crest_factor", "spectral_contrast", "spectral_rolloff"], {"spectral_rolloff": {"roll_percent": 0.5}}),
+    (8000, 256, 64, 3001, ["mfcc", "rms_energy"], {"mfcc": {"n_mels": 20, "n_mfcc": 20, "fmin": 100.0, "fmax": 3500.0}}),
+    (16000, 64, 16, 700, ["mfcc", "spectral_centroid"], {"mfcc": {"n_mels": 10, "n_mfcc": 5}}),
+    (16000, 32, 8, 300, ["spectral_centroid", "spectral_rolloff", "rms_energy"], None),
+    (16000, 128, 32, 1000, ["mfcc", "crest_factor"], {"mfcc": {"n_mels": 16, "dct_type": 3}}),
+    (48000, 4096, 1024, 20000, ["mfcc", "spectral_centroid", "rms_energy"], None),
+    (48000, 8192, 2048, 30000, ["mfcc", "spectral_rolloff", "crest_factor"], None),
+])
+def test_features_vs_oracle(eng, sr, fl, hop, n, features, fp):
+    y = synth.mixture(n, sr, seed=fl + n)
+    names, ref = oracle_rows(y, sr, features, fl, hop, fp)
+    p = _ffi.make_params(eng.lib, sr, features, fl, hop, feature_params=fp)
+    out = eng.features_host(y, eng.units_clips(1, n), p)
+    assert out.shape == (1,) + ref.shape
+    check_rows(names, out[0], ref, bin_hz=sr / fl)
+
+
+@pytest.mark.parametrize("kind", synth.EDGE_KINDS)
+def test_edge_clips_vs_oracle(eng, kind):
+    sr, fl, hop, n = 22050, 1024, 256, 6000
+    y = synth.edge_clip(kind, n, sr)
+    feats = ["mfcc", "spectral_centroid", "spectral_rolloff", "rms_energy", "crest_factor", "spectral_contrast"]
+    names, ref = oracle_rows(y, sr, feats, fl, hop, {"mfcc": {"n_mels": 40}})
+    p = _ffi.make_params(eng.lib, sr, feats, fl, hop, feature_params={"mfcc": {"n_mels": 40}})
+    out = eng.features_host(y, eng.units_clips(1, n), p)
+    # contrast is only comparable on frames without bins below the FP32 noise floor (in the reference those bins hold
+    # float64 round-off, here float32 round-off; both are noise, and both sit near the amin=1e-10 clamp)
+    S = np.abs(orc.compute_stft(y.astype(np.float64), n_fft=fl, hop_length=hop))
+    ok = (S.min(axis=0) >= 1e-5 * S.max(axis=0))          # all-zero frames stay comparable (exactly 0 dB both sides)
+    if kind in ("zeros",):
+        # all-zero frames: centroid 0, rolloff = freqs[-1], rms 0, crest 0, mfcc of a flat -80 dB... exact expectations
+        d = dict(zip(names, out[0]))
+        assert (d["spectral_centroid"] == 0).all() and (d["rms_energy"] == 0).all() and (d["crest_factor"] == 0).all()
+        assert np.allclose(d["spectral_rolloff"], sr / 2)
+    check_rows(names, out[0], ref, bin_hz=sr / fl, contrast_ok=ok)
+
+
+def test_short_and_ragged_units(eng):
+    """Units shorter than a frame (manager test: 512 samples @ frame 1024 -> 3 frames, 100 samples -> 1 frame), a ragged
+    tail (zero-padded like segment_fixed_length(pad=True)) and a unit entirely past the end of the buffer."""
+    sr, fl, hop = 22050, 1024, 256
+    y = synth.mixture(2000, sr, seed=5)
+    for n in (512, 100, 1):
+        names, ref = oracle_rows(y[:n], sr, ["mfcc", "rms_energy", "crest_factor"], fl, hop)
+        p = _ffi.make_params(eng.lib, sr, ["mfcc", "rms_energy", "crest_factor"], fl, hop)
+        out = eng.features_host(y[:n], eng.units_clips(1, n), p)
+        assert out.shape[2] == 1 + n // hop == ref.shape[1]
+        check_rows(names, out[0], ref, bin_hz=sr / fl)
+    # ragged: 3 units of 900 samples over a 2000-sample buffer; the third has 200 valid samples, a fourth none
+    p = _ffi.make_params(eng.lib, sr, ["rms_energy", "spectral_centroid", "mfcc"], fl, hop)
+    out = eng.features_host(y, eng.units_clips(4, 900, total_len=2000, stride=900), p)
+    for u in range(4):
+        seg = np.zeros(900, dtype=np.float32)
+        v = max(0, min(900, 2000 - 900 * u))
+        seg[:v] = y[900 * u:900 * u + v]
+        names, ref = oracle_rows(seg, sr, ["rms_energy", "spectral_centroid", "mfcc"], fl, hop)
+        check_rows(names, out[u], ref, bin_hz=sr / fl)
+
+
+def test_empty_and_errors(eng):
+    p = _ffi.make_params(eng.lib, 16000, ["mfcc"], 512, 160)
+    out = eng.features_host(np.zeros(0, np.float32), eng.units_clips(0, 16000), p)
+    assert out.shape == (0, 13, 101)
+    # center=False, unit shorter than a frame: zero frames, nothing written
+    p2 = _ffi.make_params(eng.lib, 16000, ["rms_energy"], 512, 160, center=False)
+    out = eng.features_host(np.zeros(100, np.float32), eng.units_clips(1, 100), p2)
+    assert out.shape == (1, 1, 0)
+    with pytest.raises(NotImplementedError):
+        eng.features_host(np.zeros(4000, np.float32), eng.units_clips(1, 4000), _ffi.make_params(eng.lib, 16000, ["mfcc"], 1000, 160))
+    with pytest.raises(ValueError):
+        eng.features_host(np.zeros(4000, np.float32), eng.units_clips(1, 4000),
+                          _ffi.make_params(eng.lib, 16000, ["mfcc"], 512, 160, feature_params={"mfcc": {"n_mfcc": 200}}))
+    with pytest.raises(ValueError):   # librosa: "Frequency band exceeds Nyquist" (sr <= 12800 with the default bands)
+        eng.features_host(np.zeros(4000, np.float32), eng.units_clips(1, 4000), _ffi.make_params(eng.lib, 8000, ["spectral_contrast"], 512, 160))
+    with pytest.raises(ValueError):
+        eng.stft_host(np.zeros(4000, np.float32), eng.units_clips(1, 4000), 512, 0, 512)
+
+
+def test_batch_equals_single_units(eng):
+    """Determinism / independence: a unit's rows do not depend on its neighbours in the batch."""
+    sr = 16000
+    clips = synth.clip_batch(9, 4000, sr, seed=77, edges=False)
+    p = _ffi.make_params(eng.lib, sr, ["mfcc", "spectral_contrast", "spectral_rolloff", "rms_energy"], 512, 160, feature_params={"mfcc": {"n_mels": 40}})
+    allout = eng.features_host(clips.ravel(), eng.units_clips(9, 4000), p)
+    for c in (0, 4, 8):
+        one = eng.features_host(clips[c], eng.units_clips(1, 4000), p)
+        assert np.array_equal(one[0], allout[c])
+
+
+def test_welch_vs_oracle_shapes(eng):
+    sr = 25600
+    y = synth.long_signal(3 * sr, sr, seed=9, block_sec=0.25)
+    for nperseg, nov, nfft in ((1024, 512, 1024), (256, 128, 256), (500, 100, 512), (64, 0, 64)):
+        u = eng.units_clips(3, sr)
+        psd = eng.psd_welch_host(y, u, sr, 0, nperseg, nov, nfft, True, 0)
+        for c in range(3):
+            f, ref = orc.compute_psd_welch(y[c * sr:(c + 1) * sr].astype(np.float64), fs=sr, nperseg=nperseg, noverlap=nov, nfft=nfft)
+            assert psd[c].shape == ref.shape
+            assert (np.abs(psd[c] - ref) <= 1e-4 * ref + 2e-6 * ref.max()).all()
