@@ -18,14 +18,8 @@
 #include <string>
 #include <vector>
 
-#include "syg_kernels.cuh"
+#include "syg_launch.h"
 #include "syg_plan.h"
-
-#ifndef SYG_EMU
-#define SYG_OCCUPANCY(nb, kernel, threads, smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(nb), kernel, threads, smem)
-#else
-#define SYG_OCCUPANCY(nb, kernel, threads, smem) ((nb) = 2, cudaSuccess)
-#endif
 
 namespace {
 
@@ -170,77 +164,25 @@ int get_window(syg_ctx* ctx, int window, int win_length, int n_fft, bool centred
 }
 
 // ---------------------------------------------------------------------------------------------- kernel dispatch
-template <class TL, int MODE>
-int launch_frame_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
-    using SM = sygdev::FrameSmem<TL>;
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        CK(cudaFuncSetAttribute(sygdev::frame_kernel<TL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
-        int nb = 0;
-        CK(SYG_OCCUPANCY(nb, (sygdev::frame_kernel<TL, MODE>), sygdev::kThreads, SM::bytes));
-        if (nb < 1) return fail(SYG_E_CUDA, "frame kernel does not fit on an SM (smem %zu)", (size_t)SM::bytes);
-        blocks_per_sm = nb;
-    }
-    const long long n_rounds = (a.n_frames + TL::F - 1) / TL::F;
-    if (n_rounds <= 0) return SYG_OK;
-    const long long cap = (long long)sm_count * blocks_per_sm;
-    const int grid = (int)std::min<long long>(n_rounds, cap);
-    auto kfn = sygdev::frame_kernel<TL, MODE>;
-    SYG_LAUNCH(kfn, grid, sygdev::kThreads, SM::bytes, st, a);
-    CK(cudaGetLastError());
-    return SYG_OK;
+// The kernels are instantiated in separate translation units (syg_launch_*.cu, compiled in parallel); they report
+// failures as a negative SYG_E_* code plus a message.
+int launch_rc(int rc, const std::string& err) { return rc == SYG_OK ? SYG_OK : fail(rc, "%s", err.c_str()); }
+
+int launch_features(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
+    std::string err;
+    if (n_fft > 2048) return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_FEATURES, a, sm_count, st, err), err);
+    constexpr unsigned extra = syg::FB_BANDWIDTH | syg::FB_FLATNESS | syg::FB_DOMINANT | syg::FB_MEAN_AMP | syg::FB_STD_AMP;
+    return launch_rc(syglaunch::frame_warp(n_fft, (a.mask & extra) != 0, a, sm_count, st, err), err);
 }
 
-template <int MODE>
-int launch_frame(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
-    using namespace sygdev;
-    switch (ilog2i(n_fft / 2)) {
-        case 4: return launch_frame_t<FftTile<4, 4>, MODE>(a, sm_count, st);
-        case 5: return launch_frame_t<FftTile<5, 8>, MODE>(a, sm_count, st);
-        case 6: return launch_frame_t<FftTile<6, 8>, MODE>(a, sm_count, st);
-        case 7: return launch_frame_t<FftTile<7, 16>, MODE>(a, sm_count, st);
-        case 8: return launch_frame_t<FftTile<8, 16>, MODE>(a, sm_count, st);
-        case 9: return launch_frame_t<FftTile<9, 16>, MODE>(a, sm_count, st);
-        case 10: return launch_frame_t<FftTile<10, 16>, MODE>(a, sm_count, st);
-        case 11: return launch_frame_t<FftTile<11, 16>, MODE>(a, sm_count, st);
-        case 12: return launch_frame_t<FftTile<12, 16>, MODE>(a, sm_count, st);
-    }
-    return fail(SYG_E_UNSUPPORTED, "n_fft=%d: only powers of two in [32, 8192] are supported", n_fft);
-}
-
-template <class TL>
-int launch_welch_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st) {
-    using SM = sygdev::WelchSmem<TL>;
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        CK(cudaFuncSetAttribute(sygdev::welch_kernel<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
-        int nb = 0;
-        CK(SYG_OCCUPANCY(nb, (sygdev::welch_kernel<TL>), sygdev::kThreads, SM::bytes));
-        if (nb < 1) return fail(SYG_E_CUDA, "welch kernel does not fit on an SM");
-        blocks_per_sm = nb;
-    }
-    if (a.g.n_units <= 0) return SYG_OK;
-    const int grid = (int)std::min<long long>(a.g.n_units, (long long)sm_count * blocks_per_sm);
-    auto kfn = sygdev::welch_kernel<TL>;
-    SYG_LAUNCH(kfn, grid, sygdev::kThreads, SM::bytes, st, a);
-    CK(cudaGetLastError());
-    return SYG_OK;
+int launch_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
+    std::string err;
+    return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_STFT, a, sm_count, st, err), err);
 }
 
 int launch_welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st) {
-    using namespace sygdev;
-    switch (ilog2i(nfft / 2)) {
-        case 4: return launch_welch_t<FftTile<4, 4>>(a, sm_count, st);
-        case 5: return launch_welch_t<FftTile<5, 8>>(a, sm_count, st);
-        case 6: return launch_welch_t<FftTile<6, 8>>(a, sm_count, st);
-        case 7: return launch_welch_t<FftTile<7, 16>>(a, sm_count, st);
-        case 8: return launch_welch_t<FftTile<8, 16>>(a, sm_count, st);
-        case 9: return launch_welch_t<FftTile<9, 16>>(a, sm_count, st);
-        case 10: return launch_welch_t<FftTile<10, 16>>(a, sm_count, st);
-        case 11: return launch_welch_t<FftTile<11, 16>>(a, sm_count, st);
-        case 12: return launch_welch_t<FftTile<12, 16>>(a, sm_count, st);
-    }
-    return fail(SYG_E_UNSUPPORTED, "nfft=%d: only powers of two in [32, 8192] are supported", nfft);
+    std::string err;
+    return launch_rc(syglaunch::welch(nfft, a, sm_count, st, err), err);
 }
 
 // ---------------------------------------------------------------------------------------------- validation
@@ -358,6 +300,12 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         if ((rc = upload_table(ctx, key + ":l", mt.len, &a.mel_len))) return rc;
         if ((rc = upload_table(ctx, key + ":o", mt.off, &a.mel_off))) return rc;
         if ((rc = upload_table(ctx, key + ":w", mt.w, &a.mel_w))) return rc;
+        sygplan::MelSlots ms;
+        if (!ctx->tables.count(key + ":pw")) sygplan::build_mel_slots(mt, ms);
+        std::vector<int4> slots(ms.desc.size() / 4);
+        for (size_t i = 0; i < slots.size(); ++i) slots[i] = make_int4(ms.desc[4 * i], ms.desc[4 * i + 1], ms.desc[4 * i + 2], ms.desc[4 * i + 3]);
+        if ((rc = upload_table(ctx, key + ":ps", slots, &a.mel_slots))) return rc;
+        if ((rc = upload_table(ctx, key + ":pw", ms.w, &a.mel_pw))) return rc;
         a.n_mels = p->n_mels;
         a.mel_power_is_2 = (p->power == 2.0);
         a.mel_half_power = (float)(0.5 * p->power);
@@ -411,7 +359,7 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
     int rc;
     {
         ProfScope ps(ctx, st, PROF_FRAME);
-        rc = launch_frame<sygdev::MODE_FEATURES>(n_fft, a, ctx->sm_count, st);
+        rc = launch_features(n_fft, a, ctx->sm_count, st);
     }
     if (rc) return rc;
     if (need_fin) {
@@ -431,9 +379,9 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
             fc.cws = f.cws + (size_t)u0 * pl.T * 2 * f.nb;
             fc.unit_max = f.unit_max + u0 * 4;
             fc.out = out + (size_t)u0 * pl.n_rows * pl.T;
-            dim3 grid((unsigned)gx, (unsigned)fc.n_units);
-            SYG_LAUNCH(sygdev::finalize_kernel, grid, dim3(sygdev::kThreads), smem, st, fc);
-            CK(cudaGetLastError());
+            std::string err;
+            const int frc = syglaunch::finalize(fc, (unsigned)gx, (unsigned)fc.n_units, smem, st, err);
+            if (frc) return fail(frc, "%s", err.c_str());
         }
     }
     return SYG_OK;
@@ -819,7 +767,7 @@ int syg_stft_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, int32
     a.n_frames = units->n_units * (long long)a.T;
     a.stft_out = out_dev;
     ProfScope ps(ctx, reinterpret_cast<cudaStream_t>(stream), PROF_FRAME);
-    return launch_frame<sygdev::MODE_STFT>(n_fft, a, ctx->sm_count, reinterpret_cast<cudaStream_t>(stream));
+    return launch_stft(n_fft, a, ctx->sm_count, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, int32_t n_fft, int32_t hop_length,
@@ -844,7 +792,7 @@ int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units,
                              c.g = chunk_geom(cu, shift);
                              c.n_frames = n * (long long)a.T;
                              c.stft_out = L.out0.p;
-                             return launch_frame<sygdev::MODE_STFT>(n_fft, c, sm, L.stream);
+                             return launch_stft(n_fft, c, sm, L.stream);
                          });
 }
 

@@ -1,0 +1,421 @@
+// sygnals_b200/csrc/syg_frame_warp.cuh
+//
+// frame_warp_kernel<TL, EXTRA>: the feature kernel for n_fft <= 2048 (M = n_fft/2 <= 1024 packed complex points).
+//
+// Warp-synchronous: G = M/E <= 32 lanes own one frame (E points per lane in registers), a warp owns FW = 32/G frames,
+// and nothing in the kernel needs a CTA barrier -- the two radix passes exchange through the warp's private slice of
+// shared memory with __syncwarp() only, so the 8 warps of a CTA (and the CTAs of an SM) overlap each other's
+// load / butterfly / epilogue phases.  Per frame:
+//
+//   framing (index arithmetic, zero padding by predicate) -> window -> radix-E DIF in registers -> exchange ->
+//   twiddle + radix-R2 in registers -> natural-order Z in smem -> real split -> |X|^2 in smem ->
+//   { mel energies, contrast peaks/valleys, centroid, rolloff, rms, crest, peak, [bandwidth, flatness, dominant, ...] }
+//
+// Shared-memory layout per frame: Z as float2[ZS] (one pad slot every E points: both the stride-E scatter of pass 1 and
+// the stride-M/R gather of pass 2 are bank-conflict free for 64-bit accesses) and |X|^2 as float[PS] (one pad word every
+// 32 bins: the blocked read of the spectral statistics is conflict free).
+//
+// Reference semantics: sygnals/core/features/manager.py:177-227,265-345 and the librosa routines of SURVEY.md 2.3.
+#pragma once
+
+#include "syg_device.cuh"
+#include "syg_kernels.cuh"
+#include "syg_params.h"
+
+namespace sygdev {
+
+template <class TL, int NT = kThreads>
+struct WarpTile {
+    static constexpr int E = TL::E, M = TL::M, G = TL::G, LOG2E = TL::LOG2E;
+    static_assert(G <= 32, "warp tile needs at most 32 lanes per frame");
+    static_assert(TL::NPASS == 2, "warp tile is a two-pass FFT");
+    static constexpr int FW = 32 / G;                         // frames per warp
+    static constexpr int R2 = TL::RLAST;                      // radix of pass 2
+    static constexpr int ZS = M + (M >> LOG2E) + 1;           // float2 slots per frame
+    static constexpr int PS = padded_size(M + 1) + 4;         // floats per frame (+4: mel taps are read in groups of 4)
+    static constexpr int kWarps = NT / 32;
+    static constexpr int warp_floats = FW * (2 * ZS + PS) + 34;   // + 32 candidate slots and a counter for the contrast selection
+    static constexpr size_t bytes = (size_t)kWarps * warp_floats * sizeof(float);
+};
+
+template <int LOG2E>
+SYG_DEVICE SYG_INLINE int zpad(int i) { return i + (i >> LOG2E); }
+
+template <int G>
+SYG_DEVICE SYG_INLINE float lanes_sum(float v) {
+    SYG_UNROLL
+    for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o, G);
+    return v;
+}
+template <int G>
+SYG_DEVICE SYG_INLINE double lanes_sum(double v) {
+    SYG_UNROLL
+    for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o, G);
+    return v;
+}
+template <int G>
+SYG_DEVICE SYG_INLINE float lanes_max(float v) {
+    SYG_UNROLL
+    for (int o = G / 2; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o, G));
+    return v;
+}
+template <int G>
+SYG_DEVICE SYG_INLINE double lanes_scan_incl(double v, int gl) {
+    SYG_UNROLL
+    for (int o = 1; o < G; o <<= 1) {
+        const double n = __shfl_up_sync(kFull, v, o, G);
+        if (gl >= o) v += n;
+    }
+    return v;
+}
+
+// SYNCP: CTA barriers at the phase boundaries.  Not needed for correctness (warps own disjoint shared-memory slices);
+// they keep the warps of a CTA inside the same code region, which is what the instruction caches want: the per-frame
+// code is ~6000 straight-line instructions, several times the L1.5 instruction cache.
+template <class TL, bool EXTRA, int NT, int MINB, bool SYNCP>
+__global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameArgs a) {
+    using WT = WarpTile<TL, NT>;
+    constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, ZS = WT::ZS, PS = WT::PS, LE = WT::LOG2E;
+    constexpr int Q = E / R2;
+    constexpr int B = M + 1;
+    SYG_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int f = lane / G, j = lane % G;
+    float* const wbase = reinterpret_cast<float*>(smem_raw) + warp * WT::warp_floats;
+    float2* const zw = reinterpret_cast<float2*>(wbase);             // [FW][ZS]
+    float* const pww = wbase + FW * 2 * ZS;                           // [FW][PS]
+    float* const cand = pww + FW * PS;                                // [32]
+    float2* const zs = zw + f * ZS;
+    float* const pf = pww + f * PS;
+
+    // pad slots / guard words of the power spectra are read (with zero weight) by the mel sweep: keep them finite
+    for (int i = lane; i < FW * PS + 34; i += 32) pww[i] = 0.0f;
+    __syncwarp();
+
+    const long long n_tasks = (a.n_frames + FW - 1) / FW;
+    // all warps of the CTA run the same number of iterations (tasks past the end are processed as empty frames)
+    for (long long task0 = (long long)blockIdx.x * WT::kWarps; task0 < n_tasks; task0 += (long long)gridDim.x * WT::kWarps) {
+        const long long task = task0 + warp;
+        const long long gf = task * FW + f;
+        const bool valid = gf < a.n_frames;
+        const long long u = valid ? gf / a.T : 0;
+        const int t = valid ? (int)(gf - u * a.T) : 0;
+        UnitRef ur = unit_ref(a.g, u);
+        if (!valid) ur.valid = 0;
+        const long long p0 = (long long)t * a.hop - a.cpad;
+
+        // ---------------- framing + window + time-domain partial statistics ----------------
+        float xr[E], xi[E];
+        float s_sq = 0.0f, s_sq2 = 0.0f, pk = 0.0f, pk2 = 0.0f;
+        double s_sum = 0.0, s_abs = 0.0, s_sqd = 0.0;
+        {
+            const float* src = a.y + ur.start + p0;
+            const bool interior = (p0 >= 0) && (p0 + 2 * M <= ur.valid) && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
+            const float2* w2 = reinterpret_cast<const float2*>(a.window);
+            if (__all_sync(kFull, interior)) {
+                SYG_UNROLL
+                for (int r = 0; r < E; ++r) {
+                    const int c = j + r * G;
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(src) + c);
+                    const float2 w = __ldg(w2 + c);
+                    s_sq = __fmaf_rn(v.x, v.x, s_sq);
+                    s_sq2 = __fmaf_rn(v.y, v.y, s_sq2);
+                    pk = fmaxf(pk, fabsf(v.x));
+                    pk2 = fmaxf(pk2, fabsf(v.y));
+                    if (EXTRA) {
+                        s_sum += (double)v.x + (double)v.y;
+                        s_abs += (double)fabsf(v.x) + (double)fabsf(v.y);
+                        s_sqd += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+                    }
+                    xr[r] = v.x * w.x;
+                    xi[r] = v.y * w.y;
+                }
+            } else {
+                // edge / unaligned frames: a compact loop stages the zero-padded samples in the (idle) Z slice first
+                float* st = reinterpret_cast<float*>(zs);
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+                for (int i = j; i < 2 * M; i += G) {
+                    const long long pos = p0 + i;
+                    st[i] = (pos >= 0 && pos < ur.valid) ? __ldg(a.y + ur.start + pos) : 0.0f;
+                }
+                __syncwarp();
+                SYG_UNROLL
+                for (int r = 0; r < E; ++r) {
+                    const int c = j + r * G;
+                    const float2 v = reinterpret_cast<const float2*>(st)[c];
+                    const float2 w = __ldg(w2 + c);
+                    s_sq = __fmaf_rn(v.x, v.x, s_sq);
+                    s_sq2 = __fmaf_rn(v.y, v.y, s_sq2);
+                    pk = fmaxf(pk, fabsf(v.x));
+                    pk2 = fmaxf(pk2, fabsf(v.y));
+                    if (EXTRA) {
+                        s_sum += (double)v.x + (double)v.y;
+                        s_abs += (double)fabsf(v.x) + (double)fabsf(v.y);
+                        s_sqd += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+                    }
+                    xr[r] = v.x * w.x;
+                    xi[r] = v.y * w.y;
+                }
+                __syncwarp();
+            }
+        }
+
+        if (SYNCP) __syncthreads();
+        // ---------------- pass 1: radix E, no twiddles; butterfly j scatters to j*E + k' ----------------
+        dft_dif<E, 1>(xr, xi);
+        SYG_UNROLL
+        for (int kp = 0; kp < E; ++kp) {
+            const int src = bitrev(kp, LE);
+            zs[zpad<LE>(j * E + kp)] = make_float2(xr[src], xi[src]);
+        }
+        __syncwarp();
+        // ---------------- pass 2: Q butterflies of radix R2 per lane, twiddles W_M^{r k} ----------------
+        SYG_UNROLL
+        for (int q = 0; q < Q; ++q) {
+            const int b = j + q * G;
+            SYG_UNROLL
+            for (int r = 0; r < R2; ++r) {
+                const float2 v = zs[zpad<LE>(b + r * (M / R2))];
+                xr[q * R2 + r] = v.x;
+                xi[q * R2 + r] = v.y;
+            }
+        }
+        __syncwarp();
+        if (SYNCP) __syncthreads();
+        SYG_UNROLL
+        for (int q = 0; q < Q; ++q) {
+            const int b = j + q * G;
+            const int k = b & (E - 1);                                 // NS = E
+            constexpr int SH = TL::LOG2M - ilog2(E * R2);             // = 0: W_{E*R2} = W_M
+            SYG_UNROLL
+            for (int r = 1; r < R2; ++r) {
+                const float2 w = __ldg(&a.tw[(r * k) << SH]);
+                cmul(xr[q * R2 + r], xi[q * R2 + r], w.x, w.y);
+            }
+            dft_dif<R2, 1>(xr + q * R2, xi + q * R2);
+            const int ob = (b - k) * R2 + k;
+            SYG_UNROLL
+            for (int kp = 0; kp < R2; ++kp) {
+                const int src = q * R2 + bitrev(kp, ilog2(R2));
+                zs[zpad<LE>(ob + kp * E)] = make_float2(xr[src], xi[src]);
+            }
+        }
+        __syncwarp();
+
+        if (SYNCP) __syncthreads();
+        // ---------------- real split -> |X[k]|^2 ----------------
+        SYG_UNROLL
+        for (int i = 0; i <= E / 2; ++i) {
+            const int k = j + i * G;
+            if (i == E / 2 && j != 0) break;
+            const int km = (M - k) & (M - 1);
+            const float2 zk = zs[zpad<LE>(k)], zm = zs[zpad<LE>(km)];
+            const float2 w = __ldg(&a.tws[k]);
+            float xkr, xki, xmr, xmi;
+            real_split(zk.x, zk.y, zm.x, zm.y, w.x, w.y, xkr, xki, xmr, xmi);
+            const int k2 = M - k;
+            pf[padi(k)] = __fmaf_rn(xkr, xkr, xki * xki);
+            if (k2 != k) pf[padi(k2)] = __fmaf_rn(xmr, xmr, xmi * xmi);
+        }
+        __syncwarp();
+
+        float* const orow = a.out + (long long)u * a.n_rows * a.T + t;
+
+        // ---------------- time-domain features (unwindowed, zero-padded frame) ----------------
+        if (a.mask & syg::FB_TIME_ANY) {
+            const float tsq = lanes_sum<G>(s_sq + s_sq2);
+            const float tpk = lanes_max<G>(fmaxf(pk, pk2));
+            if (j == 0 && valid) {
+                const float rms = sqrtf(tsq * (1.0f / (float)TL::NFFT));
+                if (a.row_rms >= 0) orow[(long long)a.row_rms * a.T] = rms;
+                if (a.row_crest >= 0) orow[(long long)a.row_crest * a.T] = ((double)rms < kEps64) ? 0.0f : tpk / rms;
+                if (a.row_peak >= 0) orow[(long long)a.row_peak * a.T] = tpk;
+            }
+            if (EXTRA) {
+                if (a.mask & (syg::FB_STD_AMP | syg::FB_MEAN_AMP)) {
+                    const double tsum = lanes_sum<G>(s_sum), tabs = lanes_sum<G>(s_abs), tsqd = lanes_sum<G>(s_sqd);
+                    if (j == 0 && valid) {
+                        const double n = (double)TL::NFFT;
+                        if (a.row_mean_amp >= 0) orow[(long long)a.row_mean_amp * a.T] = (float)(tabs / n);
+                        if (a.row_std_amp >= 0) {
+                            const double mu = tsum / n;
+                            double var = tsqd / n - mu * mu;
+                            if (var < 0.0) var = 0.0;
+                            orow[(long long)a.row_std_amp * a.T] = (float)sqrt(var);
+                        }
+                    }
+                }
+            }
+        }
+
+        if (SYNCP) __syncthreads();
+        // ---------------- per-frame spectral statistics (lane j owns bins [j*E, j*E+E), last lane also bin M) ----------------
+        if (a.mask & syg::FB_SPECSTATS) {
+            const int k0 = j * E;
+            const float* pb = pf + padi(k0);                            // bin k0 + i at pb[i] (i < E <= 32)
+            double sp = 0.0, sp1 = 0.0;
+            float sm = 0.0f, skm = 0.0f, slog = 0.0f, sm1 = 0.0f, skm1 = 0.0f;
+            float vmax = -1.0f;
+            int imax = 0;
+            const float kf0 = (float)k0;
+            SYG_UNROLL
+            for (int i = 0; i < E; ++i) {
+                const float p = pb[i];
+                const float mg = sqrt_approx(p);
+                if (i & 1) { sp1 += (double)p; sm1 += mg; skm1 = __fmaf_rn(mg, kf0 + (float)i, skm1); }
+                else { sp += (double)p; sm += mg; skm = __fmaf_rn(mg, kf0 + (float)i, skm); }
+                if (EXTRA) {
+                    if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p) + 2.220446049250313e-16f);
+                    if (p > vmax) { vmax = p; imax = k0 + i; }
+                }
+            }
+            sp += sp1; sm += sm1; skm += skm1;
+            const float p_ny = pf[padi(M)];
+            if (j == G - 1) {                                            // bin M (Nyquist)
+                const float mg = sqrt_approx(p_ny);
+                sp += (double)p_ny;
+                sm += mg;
+                skm = __fmaf_rn(mg, (float)M, skm);
+                if (EXTRA) {
+                    if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p_ny) + 2.220446049250313e-16f);
+                    if (p_ny > vmax) { vmax = p_ny; imax = M; }
+                }
+            }
+            const int nk = E + ((j == G - 1) ? 1 : 0);
+            const double incl = lanes_scan_incl<G>(sp, j);
+            const double total_p = __shfl_sync(kFull, incl, G - 1, G);
+            double prev = __shfl_up_sync(kFull, incl, 1, G);
+            if (j == 0) prev = -1.0;
+            const float tm = lanes_sum<G>(sm);
+            const float tkm = lanes_sum<G>(skm);
+            double centroid_hz = 0.0;
+            if ((double)tm >= kEps64) centroid_hz = a.bin_hz * ((double)tkm / (double)tm);
+            if (a.row_centroid >= 0 && j == 0 && valid) orow[(long long)a.row_centroid * a.T] = (float)centroid_hz;
+            if (a.row_rolloff >= 0) {
+                if (total_p < kEps64) {
+                    if (j == 0 && valid) orow[(long long)a.row_rolloff * a.T] = (float)(a.bin_hz * (double)M);
+                } else {
+                    const double thr = a.roll_percent * total_p;
+                    if (incl >= thr && prev < thr) {                   // exactly one lane of the group
+                        double c = (j == 0) ? 0.0 : prev;
+                        int bin = k0 + nk - 1;
+                        for (int i = 0; i < nk; ++i) {
+                            c += (double)pf[padi(k0 + i)];
+                            if (c >= thr) { bin = k0 + i; break; }
+                        }
+                        if (valid) orow[(long long)a.row_rolloff * a.T] = (float)(a.bin_hz * (double)bin);
+                    }
+                }
+            }
+            if (EXTRA) {
+                if (a.row_flatness >= 0) {
+                    const float tl = lanes_sum<G>(slog);
+                    if (j == 0 && valid) {
+                        const double am = (double)tm / (double)B;
+                        double fl = 0.0;
+                        if (am >= kEps64) {
+                            fl = exp((double)tl / (double)B) / am;
+                            fl = fl < 0.0 ? 0.0 : (fl > 1.0 ? 1.0 : fl);
+                        }
+                        orow[(long long)a.row_flatness * a.T] = (float)fl;
+                    }
+                }
+                if (a.row_bandwidth >= 0) {
+                    double sb = 0.0;
+                    for (int i = 0; i < nk; ++i) {
+                        const double mg = (double)sqrtf(pf[padi(k0 + i)]);
+                        const double d = a.bin_hz * (double)(k0 + i) - centroid_hz;
+                        sb += mg * d * d;
+                    }
+                    const double tb = lanes_sum<G>(sb);
+                    if (j == 0 && valid) orow[(long long)a.row_bandwidth * a.T] = ((double)tm < kEps64) ? 0.0f : (float)sqrt(tb / (double)tm);
+                }
+                if (a.row_dominant >= 0) {
+                    const float gmax = lanes_max<G>(vmax);
+                    float mi = (vmax == gmax) ? -(float)imax : -1.0e9f;
+                    mi = lanes_max<G>(mi);
+                    if (j == 0 && valid) orow[(long long)a.row_dominant * a.T] = (float)(a.bin_hz * (double)(-mi));
+                }
+            }
+        }
+
+        if (SYNCP) __syncthreads();
+        // ---------------- mel energies: lanes sweep (frame, slot) pairs; slots are filters sorted by span ----------------
+        if (a.mask & syg::FB_MFCC) {
+            float fmx[FW];
+            SYG_UNROLL
+            for (int ff = 0; ff < FW; ++ff) fmx[ff] = 0.0f;
+            const int ntask = FW * a.n_mels;
+            for (int base = 0; base < ntask; base += 32) {
+                const int mt = base + lane;
+                if (mt < ntask) {
+                    const int ff = (FW == 1) ? 0 : mt / a.n_mels;
+                    const int slot = mt - ff * a.n_mels;
+                    const long long gff = task * FW + ff;
+                    if (gff < a.n_frames) {
+                        const int4 d = __ldg(&a.mel_slots[slot]);       // {filter, padded start, taps, offset}
+                        const float4* wv = reinterpret_cast<const float4*>(a.mel_pw + d.w);
+                        const float* pp = pww + ff * PS + d.y;
+                        float acc = 0.0f;
+                        if (a.mel_power_is_2) {
+                            float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                            for (int i = 0; i < d.z; i += 4) {
+                                const float4 w = __ldg(wv + (i >> 2));
+                                acc = __fmaf_rn(w.x, pp[i], acc);
+                                a1 = __fmaf_rn(w.y, pp[i + 1], a1);
+                                a2 = __fmaf_rn(w.z, pp[i + 2], a2);
+                                a3 = __fmaf_rn(w.w, pp[i + 3], a3);
+                            }
+                            acc = (acc + a1) + (a2 + a3);
+                        } else {
+                            for (int i = 0; i < d.z; ++i)
+                                acc = __fmaf_rn(__ldg(a.mel_pw + d.w + i), powf(pp[i], a.mel_half_power), acc);
+                        }
+                        a.melws[gff * a.n_mels + d.x] = acc;
+                        SYG_UNROLL
+                        for (int q = 0; q < FW; ++q) if (q == ff) fmx[q] = fmaxf(fmx[q], acc);
+                    }
+                }
+            }
+            SYG_UNROLL
+            for (int ff = 0; ff < FW; ++ff) {
+                const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fmx[ff], 0.0f)));
+                const long long gff = task * FW + ff;
+                if (lane == 0 && gff < a.n_frames && mx != 0u) atomicMax(&a.unit_max[(gff / a.T) * 4 + 0], mx);
+            }
+        }
+
+        if (SYNCP) __syncthreads();
+        // ---------------- spectral contrast: per band mean of the n largest / n smallest magnitudes ----------------
+        if (a.mask & syg::FB_CONTRAST) {
+            for (int ff = 0; ff < FW; ++ff) {
+                const long long gff = task * FW + ff;
+                if (gff >= a.n_frames) break;
+                const float* pp = pww + ff * PS;
+                float pmx = 0.0f, vmx = 0.0f;
+                for (int bd = 0; bd < a.nb; ++bd) {
+                    float peak, valley;
+                    band_extremes_any(pp, a.band_lo[bd], a.band_cnt[bd], a.band_n[bd], reinterpret_cast<unsigned*>(cand), peak, valley);
+                    if (lane == 0) {
+                        a.cws[gff * (2 * a.nb) + bd] = peak;
+                        a.cws[gff * (2 * a.nb) + a.nb + bd] = valley;
+                    }
+                    if (peak == peak) pmx = fmaxf(pmx, peak);
+                    if (valley == valley) vmx = fmaxf(vmx, valley);
+                }
+                if (lane == 0) {
+                    unsigned* um = a.unit_max + (gff / a.T) * 4;
+                    if (pmx > 0.0f) atomicMax(&um[1], __float_as_uint(pmx));
+                    if (vmx > 0.0f) atomicMax(&um[2], __float_as_uint(vmx));
+                }
+            }
+        }
+        __syncwarp();                                                   // smem slices are reused by the next task
+        if (SYNCP) __syncthreads();
+    }
+}
+
+}  // namespace sygdev

@@ -1,0 +1,14 @@
+// sygnals_b200/csrc/syg_launch.h -- host-side launch interface between syg_api.cu and the kernel translation units.
+#pragma once
+
+#include <string>
+
+#include "syg_params.h"
+
+namespace syglaunch {
+// all return 0 or a negative SYG_E_* code (-3 CUDA, -5 unsupported) with a message in err
+int frame_block(int n_fft, int mode, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
+int frame_warp(int n_fft, bool extra, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
+int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err);
+int welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err);
+}  // namespace syglaunch

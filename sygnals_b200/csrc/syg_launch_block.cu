@@ -1,0 +1,59 @@
+// CTA-synchronous frame kernel instantiations: STFT (all sizes) and features for n_fft 4096 / 8192, plus finalize.
+#include "syg_launch_common.h"
+#include "syg_kernels.cuh"
+#include "syg_finalize.cuh"
+
+namespace syglaunch {
+
+template <class TL, int MODE>
+static int frame_block_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
+    using SM = sygdev::FrameSmem<TL>;
+    static int blocks_per_sm = 0;
+    auto kfn = sygdev::frame_kernel<TL, MODE>;
+    if (blocks_per_sm == 0) {
+        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
+        int nb = 0;
+        LCK(SYG_OCCUPANCY(nb, kfn, sygdev::kThreads, SM::bytes));
+        if (nb < 1) { err = "frame kernel does not fit on an SM"; return -3; }
+        blocks_per_sm = nb;
+    }
+    const long long n_rounds = (a.n_frames + TL::F - 1) / TL::F;
+    if (n_rounds <= 0) return 0;
+    const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm);
+    SYG_LAUNCH(kfn, grid, sygdev::kThreads, SM::bytes, st, a);
+    LCK(cudaGetLastError());
+    return 0;
+}
+
+int frame_block(int n_fft, int mode, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
+    using namespace sygdev;
+    const int l = ilog2i(n_fft / 2);
+    if (mode == MODE_STFT) {
+        switch (l) {
+            case 4: return frame_block_t<FftTile<4, 4>, MODE_STFT>(a, sm_count, st, err);
+            case 5: return frame_block_t<FftTile<5, 8>, MODE_STFT>(a, sm_count, st, err);
+            case 6: return frame_block_t<FftTile<6, 8>, MODE_STFT>(a, sm_count, st, err);
+            case 7: return frame_block_t<FftTile<7, 16>, MODE_STFT>(a, sm_count, st, err);
+            case 8: return frame_block_t<FftTile<8, 16>, MODE_STFT>(a, sm_count, st, err);
+            case 9: return frame_block_t<FftTile<9, 16>, MODE_STFT>(a, sm_count, st, err);
+            case 10: return frame_block_t<FftTile<10, 16>, MODE_STFT>(a, sm_count, st, err);
+            case 11: return frame_block_t<FftTile<11, 16>, MODE_STFT>(a, sm_count, st, err);
+            case 12: return frame_block_t<FftTile<12, 16>, MODE_STFT>(a, sm_count, st, err);
+        }
+    } else {
+        switch (l) {
+            case 11: return frame_block_t<FftTile<11, 16>, MODE_FEATURES>(a, sm_count, st, err);
+            case 12: return frame_block_t<FftTile<12, 16>, MODE_FEATURES>(a, sm_count, st, err);
+        }
+    }
+    err = "n_fft=" + std::to_string(n_fft) + ": only powers of two in [32, 8192] are supported";
+    return -5;
+}
+
+int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err) {
+    SYG_LAUNCH(sygdev::finalize_kernel, dim3(grid_x, grid_y), dim3(sygdev::kThreads), smem, st, a);
+    LCK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace syglaunch

@@ -3,6 +3,13 @@
 
 #include "syg_platform.h"
 
+namespace sygdev {
+constexpr int kThreads = 256;               // threads per CTA of every kernel
+constexpr int MODE_FEATURES = 0;            // frame kernel modes
+constexpr int MODE_STFT = 1;
+constexpr int kFinTT = 32;                  // frames per finalize CTA
+}  // namespace sygdev
+
 namespace syg {
 
 // feature bits (kernel-internal; the public ids live in include/sygb200.h)
@@ -48,6 +55,8 @@ struct FrameArgs {
     const int* mel_len;         // [n_mels]
     const int* mel_off;         // [n_mels] offset into mel_w
     const float* mel_w;
+    const int4* mel_slots;      // [n_mels] {filter, padded start, taps (multiple of 4), offset into mel_pw}, longest first
+    const float* mel_pw;        // tap weights in padded-spectrum index space
     int mel_power_is_2;
     float mel_half_power;       // power / 2 (applied to |X|^2)
     int nb;                     // contrast bands incl. top (0 = off)

@@ -7,6 +7,7 @@
 //   bands       librosa.feature.spectral_contrast octave-band membership and quantile counts         (A.7)
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <string>
@@ -119,6 +120,38 @@ inline bool build_mel(double sr, int n_fft, int n_mels, double fmin, double fmax
     }
     if (t.w.empty()) t.w.push_back(0.0f);
     return true;
+}
+
+// Mel filters re-expressed for the warp kernel: "slots" sorted by span (longest first, so the 32 lanes of a warp
+// sweep filters of similar length), taps indexed in the PADDED power-spectrum space (padi(k) = k + k/32, a zero
+// weight at every pad position) and padded to a multiple of 4 taps.  desc = {filter m, padded start, taps, offset}.
+struct MelSlots { std::vector<int> desc; std::vector<float> w; };
+
+inline void build_mel_slots(const MelTable& t, MelSlots& s) {
+    std::vector<int> order(t.n_mels);
+    for (int i = 0; i < t.n_mels; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return t.len[a] > t.len[b]; });
+    s.desc.clear(); s.w.clear();
+    for (int m : order) {
+        int pst = 0, ln4 = 0;
+        const int off = (int)s.w.size();
+        if (t.len[m] > 0) {
+            const int k0 = t.start[m], k1 = t.start[m] + t.len[m] - 1;
+            pst = k0 + (k0 >> 5);
+            const int pend = k1 + (k1 >> 5);
+            ln4 = ((pend - pst + 1) + 3) / 4 * 4;
+            for (int p = pst; p < pst + ln4; ++p) {
+                float wv = 0.0f;
+                if (p <= pend && (p % 33) != 32) {
+                    const int k = 32 * (p / 33) + (p % 33);
+                    wv = t.w[t.off[m] + (k - k0)];
+                }
+                s.w.push_back(wv);
+            }
+        }
+        s.desc.push_back(m); s.desc.push_back(pst); s.desc.push_back(ln4); s.desc.push_back(off);
+    }
+    if (s.w.empty()) s.w.push_back(0.0f);
 }
 
 // rows [n_out][n_mels] of the DCT scipy.fftpack.dct(x, type, norm) restricted to the first n_out outputs,

@@ -19,6 +19,7 @@
 #define SYG_HD
 #define SYG_DEVICE
 #define SYG_INLINE inline
+#define SYG_NOINLINE static inline
 #define SYG_UNROLL
 #else
 #include <cuda_runtime.h>
@@ -28,5 +29,6 @@
 #define SYG_HD __host__ __device__
 #define SYG_DEVICE __device__
 #define SYG_INLINE __forceinline__
+#define SYG_NOINLINE static __noinline__
 #define SYG_UNROLL _Pragma("unroll")
 #endif

@@ -14,11 +14,25 @@ def build_emu(force: bool = False) -> str:
     deps.append(os.path.join(ROOT, "include", "sygb200.h"))
     if not force and os.path.exists(OUT) and all(os.path.getmtime(p) <= os.path.getmtime(OUT) for p in deps):
         return OUT
-    cmd = ["g++", "-O2", "-std=c++17", "-DSYG_EMU", "-fPIC", "-shared", "-pthread", "-I", HERE, "-I", CSRC,
-           "-Wno-unused-value", "-o", OUT + ".tmp", "-x", "c++", os.path.join(CSRC, "syg_api.cu"), os.path.join(HERE, "syg_emu.cpp")]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(ROOT, "build", "emu_obj")
+    os.makedirs(objdir, exist_ok=True)
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")] + [os.path.join(HERE, "syg_emu.cpp")]
+
+    def cc(src):
+        obj = os.path.join(objdir, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        cmd = ["g++", "-O2", "-std=c++17", "-DSYG_EMU", "-fPIC", "-pthread", "-I", HERE, "-I", CSRC, "-Wno-unused-value",
+               "-c", "-o", obj, "-x", "c++", src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ (emulator build) failed on {src}:\n" + r.stdout + r.stderr[-6000:])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        objs = list(ex.map(cc, srcs))
+    r = subprocess.run(["g++", "-shared", "-pthread", "-o", OUT + ".tmp"] + objs, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("g++ (emulator build) failed:\n" + r.stdout + r.stderr[-6000:])
+        raise RuntimeError("g++ (emulator link) failed:\n" + r.stdout + r.stderr[-6000:])
     os.replace(OUT + ".tmp", OUT)
     return OUT
 
