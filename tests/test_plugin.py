@@ -1,0 +1,113 @@
+"""The sygnals-b200 plugin against the reference's own plugin machinery (build container: the UNMODIFIED reference loader /
+registry from /root/reference) and, on the GPU box, the routed callables against the oracle."""
+import logging
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+from sygnals_b200 import plugin as plg
+
+needs_ref = pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_manifest_matches_class():
+    import tomllib
+    with open(os.path.join(ROOT, "sygnals_b200", "plugin.toml"), "rb") as f:
+        man = tomllib.load(f)
+    p = plg.SygnalsB200Plugin()
+    assert man["name"] == p.name == "sygnals-b200"
+    assert man["version"] == p.version
+    mod, cls = man["entry_point"].split(":")
+    assert mod == "sygnals_b200.plugin" and getattr(plg, cls) is plg.SygnalsB200Plugin
+    with open(os.path.join(ROOT, "pyproject.toml"), "rb") as f:
+        proj = tomllib.load(f)
+    assert proj["project"]["entry-points"]["sygnals.plugins"]["sygnals-b200"] == man["entry_point"]
+
+
+@needs_ref
+def test_reference_loader_accepts_the_plugin_and_rebinding_round_trips():
+    logging.disable(logging.CRITICAL)
+    try:
+        ref_loader.load_reference()
+        from pathlib import Path
+        from sygnals.plugins import loader as L
+        from sygnals.plugins.api import PluginRegistry, SygnalsPluginBase
+        from sygnals.config.models import SygnalsConfig
+        from sygnals.version import __version__ as core_version
+        import importlib
+        importlib.reload(plg)                                   # pick up the real SygnalsPluginBase
+        assert issubclass(plg.SygnalsB200Plugin, SygnalsPluginBase)
+        mpath = Path(ROOT) / "sygnals_b200" / "plugin.toml"
+        man = L._parse_manifest(mpath)                          # loader.py:63-83: required keys present
+        assert man is not None
+        assert L._check_compatibility(man["name"], man["version"], man["sygnals_api"], core_version)
+        import sygnals.cli.features_cmd as fc
+        import sygnals.cli.segment_cmd as sc
+        import sygnals.core.dsp as dsp
+        import sygnals.core.features.manager as mgr
+        orig = (mgr.extract_features, fc.extract_features, dsp.compute_stft, sc.segment_fixed_length)
+        reg = PluginRegistry()
+        ld = L.PluginLoader(SygnalsConfig(), reg)
+        ld.plugin_manifests[man["name"]] = (man, None)          # as discover_and_load() records an entry-point plugin
+        ld.plugin_sources[man["name"]] = "entry_point"
+        ld._load_and_register(man["name"])                      # loader.py:210-288: setup + 9 register hooks
+        assert "sygnals-b200" in ld.loaded_plugins
+        inst = ld.loaded_plugins["sygnals-b200"]
+        assert "b200_mfcc" in reg.list_features() and "b200_stft" in reg.list_transforms()
+        # the imported copies the CLI calls are rebound, not just the defining modules
+        assert fc.extract_features is mgr.extract_features and fc.extract_features is not orig[1]
+        assert fc.extract_features.__wrapped_reference__ is orig[0]
+        assert dsp.compute_stft is not orig[2] and sc.segment_fixed_length is not orig[3]
+        # unsupported features stay on the reference path (routed to the ORIGINAL function, bit-identical result)
+        y = np.sin(np.arange(4000) * 0.05)
+        a = fc.extract_features(y, 22050, ["zero_crossing_rate"], frame_length=512, hop_length=128, output_format="dict_of_arrays")
+        b = orig[0](y, 22050, ["zero_crossing_rate"], frame_length=512, hop_length=128, output_format="dict_of_arrays")
+        np.testing.assert_array_equal(a["zero_crossing_rate"], b["zero_crossing_rate"])
+        a = dsp.compute_stft(y, n_fft=300)                      # non power of two -> reference
+        np.testing.assert_array_equal(a, orig[2](y, n_fft=300))
+        # error contract unchanged (manager.py:141-143)
+        with pytest.raises(ValueError, match="Unknown feature"):
+            fc.extract_features(y, 22050, ["nope"])
+        # segmentation is integer work: the engine's table must reproduce the reference list exactly (no GPU needed)
+        segs_a = sc.segment_fixed_length(y, 1000, 1.0, overlap_ratio=0.5)
+        segs_b = orig[3](y, 1000, 1.0, overlap_ratio=0.5)
+        assert len(segs_a) == len(segs_b) and all(np.array_equal(p, q) for p, q in zip(segs_a, segs_b))
+        inst.teardown()
+        assert (mgr.extract_features, fc.extract_features, dsp.compute_stft, sc.segment_fixed_length) == orig
+    finally:
+        logging.disable(logging.NOTSET)
+
+
+def test_strict_mode_refuses_unsupported_instead_of_falling_back():
+    p = plg.SygnalsB200Plugin()
+    p._strict = True
+    fn = p.make_extract_features(original=lambda *a, **k: pytest.fail("must not reach the reference"))
+    with pytest.raises(NotImplementedError, match="no CUDA kernel"):
+        fn(np.zeros(4096), 22050, ["zero_crossing_rate"])
+    with pytest.raises(NotImplementedError, match="power of two"):
+        fn(np.zeros(4096), 22050, ["mfcc"], frame_length=1000)
+
+
+@pytest.mark.gpu
+def test_routed_extract_features_matches_oracle_on_gpu():
+    from oracle import sygnals_oracle as orc
+    from sygnals_b200.utils import synth
+    p = plg.SygnalsB200Plugin()
+    fn = p.make_extract_features(original=None)
+    sr = 22050
+    y = synth.mixture(3 * sr, sr, seed=7).astype(np.float64)
+    feats = ["mfcc", "rms_energy", "spectral_centroid"]
+    got = fn(y, sr, feats, output_format="dict_of_arrays")
+    ref = orc.extract_features(y, sr, feats)
+    assert list(got) == list(ref)
+    np.testing.assert_array_equal(got["time"], ref["time"])
+    for k in ref:
+        if k.startswith("mfcc"):
+            np.testing.assert_allclose(got[k], ref[k], atol=1e-3, rtol=0)         # abs 1e-3 on MFCC (north_star)
+        elif k != "time":
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-5, atol=1e-7)
+    df = fn(y, sr, feats)                                                         # DataFrame contract (manager.py:430-442)
+    assert df.index.name == "time" and list(df.columns) == [k for k in ref if k != "time"]
