@@ -301,7 +301,7 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         if ((rc = upload_table(ctx, key + ":o", mt.off, &a.mel_off))) return rc;
         if ((rc = upload_table(ctx, key + ":w", mt.w, &a.mel_w))) return rc;
         sygplan::MelSlots ms;
-        if (!ctx->tables.count(key + ":pw")) sygplan::build_mel_slots(mt, ms);
+        if (!ctx->tables.count(key + ":pw")) sygplan::build_mel_slots(mt, ms, fl / 2 + 1);
         std::vector<int4> slots(ms.desc.size() / 4);
         for (size_t i = 0; i < slots.size(); ++i) slots[i] = make_int4(ms.desc[4 * i], ms.desc[4 * i + 1], ms.desc[4 * i + 2], ms.desc[4 * i + 3]);
         if ((rc = upload_table(ctx, key + ":ps", slots, &a.mel_slots))) return rc;

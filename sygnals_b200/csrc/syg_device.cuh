@@ -404,7 +404,7 @@ SYG_DEVICE SYG_INLINE float sqrt_approx(float x) {
     return std::sqrt(x);
 #else
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 #endif
 }
@@ -604,6 +604,259 @@ SYG_DEVICE SYG_INLINE void band_extremes_small(const float* __restrict__ p, int 
     const float inv_n = 1.0f / (float)n;
     peak = res[0] * inv_n;
     valley = res[1] * inv_n;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// warp kernel, second generation of the spectral-contrast selection (everything in registers, no shared-memory
+// candidate list).  P spectra of the warp kernel use 4 pad words per 32 bins:
+// --------------------------------------------------------------------------------------------------------
+SYG_DEVICE SYG_INLINE int ppad(int k) { return k + ((k >> 5) << 2); }
+
+// peak / valley of one spectral-contrast band for a full warp: mean magnitude of the n largest / n smallest |X|^2 bins
+// of p[ppad(lo + i)], i < count, 1 <= n <= count.
+//
+// Streaming selection.  The band is lane-striped (element i belongs to lane i % 32, consecutive elements of a lane are
+// 36 words apart in the ppad layout).  While streaming the band once from shared memory every lane keeps the 4 largest
+// keys of BOTH directions sorted in registers (top: key = bits(x); bottom: key = ~bits(x); order preserving for
+// non-negative floats; 0 = "nothing").  Extraction then works on the lanes' sorted heads:
+//   bulk round : M2 = warp max of the second entries; every head > M2 is larger than all non-head elements, so the
+//                set {a0 > M2} is exactly the |S| largest remaining elements -> all of them pop in one step
+//                (each lane sums its own popped values; one warp reduction at the end);
+//   single pop : when a bulk round would overshoot n or is blocked by a tie, the warp maximum pops alone; ties are
+//                counted by value, so silent frames finish in one step.
+// A lane that has popped its 4 tracked keys re-streams its elements below the last popped key (rare).  Exact.
+SYG_DEVICE SYG_INLINE void cex(unsigned& lo_, unsigned& hi_) {        // compare-exchange: lo_ <= hi_ afterwards
+    const unsigned l = min(lo_, hi_), h = max(lo_, hi_);
+    lo_ = l; hi_ = h;
+}
+// insert v into the descending list t0 >= t1 >= t2 >= t3 (largest four)
+SYG_DEVICE SYG_INLINE void ins4_desc(unsigned& t0, unsigned& t1, unsigned& t2, unsigned& t3, unsigned v) {
+    unsigned h;
+    h = max(t0, v); v = min(t0, v); t0 = h;
+    h = max(t1, v); v = min(t1, v); t1 = h;
+    h = max(t2, v); v = min(t2, v); t2 = h;
+    t3 = max(t3, v);
+}
+// insert v into the ascending list t0 <= t1 <= t2 <= t3 (smallest four)
+SYG_DEVICE SYG_INLINE void ins4_asc(unsigned& t0, unsigned& t1, unsigned& t2, unsigned& t3, unsigned v) {
+    unsigned l;
+    l = min(t0, v); v = max(t0, v); t0 = l;
+    l = min(t1, v); v = max(t1, v); t1 = l;
+    l = min(t2, v); v = max(t2, v); t2 = l;
+    t3 = min(t3, v);
+}
+
+struct Sel4 {                        // one lane's view of a band: four largest (a, descending) and four smallest (b, ascending)
+    unsigned a0, a1, a2, a3, b0, b1, b2, b3;
+};
+
+// stream this lane's `mine` elements (q[36 i]) once, keeping both sorted quadruples.  Elements are taken four at a time:
+// a 5-exchange sorting network orders the quad, two bitonic half-merges fold it into the lists (8.5 min/max per element
+// instead of 14 for element-wise insertion).
+SYG_DEVICE SYG_INLINE Sel4 track4(const float* __restrict__ q, int mine, int count) {
+    Sel4 t;
+    t.a0 = t.a1 = t.a2 = t.a3 = 0u;
+    t.b0 = t.b1 = t.b2 = t.b3 = 0xffffffffu;
+    // warp-uniform trip counts: every lane owns at least count/32 elements and at most one more
+    const int nq = (count >> 5) >> 2;                           // full quads every lane has
+    const int nmax = (count + 31) >> 5;
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+    for (int i = 0; i < nq; ++i) {
+        const float* e = q + 144 * i;
+        unsigned s0 = __float_as_uint(e[0]), s1 = __float_as_uint(e[36]), s2 = __float_as_uint(e[72]), s3 = __float_as_uint(e[108]);
+        cex(s0, s1); cex(s2, s3); cex(s0, s2); cex(s1, s3); cex(s1, s2);          // s0 <= s1 <= s2 <= s3
+        // largest four of {a} U {s}: max(a_i, s_i) is bitonic and holds them; two exchange stages sort it descending
+        unsigned l0 = max(t.a0, s0), l1 = max(t.a1, s1), l2 = max(t.a2, s2), l3 = max(t.a3, s3);
+        cex(l2, l0); cex(l3, l1); cex(l1, l0); cex(l3, l2);
+        t.a0 = l0; t.a1 = l1; t.a2 = l2; t.a3 = l3;
+        // smallest four of {b} U {s}: min(b_i, s_{3-i}); sort ascending
+        unsigned m0 = min(t.b0, s3), m1 = min(t.b1, s2), m2 = min(t.b2, s1), m3 = min(t.b3, s0);
+        cex(m0, m2); cex(m1, m3); cex(m0, m1); cex(m2, m3);
+        t.b0 = m0; t.b1 = m1; t.b2 = m2; t.b3 = m3;
+    }
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+    for (int i = 4 * nq; i < nmax; ++i) {                        // <= 4 steps; the last one may be missing in some lanes
+        const bool have = i < mine;
+        const unsigned x = have ? __float_as_uint(q[36 * i]) : 0u;
+        ins4_desc(t.a0, t.a1, t.a2, t.a3, x);
+        ins4_asc(t.b0, t.b1, t.b2, t.b3, have ? x : 0xffffffffu);
+    }
+    return t;
+}
+
+// rebuild a lane's descending quadruple from its elements below `last` (keys = bits ^ flip) plus the copies of `last`
+// it has not popped yet; popped = number of elements this lane has popped so far (they are its `popped` largest keys)
+SYG_DEVICE SYG_INLINE uint4 refill4(const float* __restrict__ q, int mine, unsigned flip, unsigned last, int popped) {
+    unsigned n0 = 0u, n1 = 0u, n2 = 0u, n3 = 0u;
+    int ge = 0;
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+    for (int i = 0; i < mine; ++i) {
+        const unsigned x = __float_as_uint(q[36 * i]) ^ flip;
+        ge += (x >= last) ? 1 : 0;
+        ins4_desc(n0, n1, n2, n3, (x < last) ? x : 0u);
+    }
+    for (int r = min(ge - popped, 4); r > 0; --r) ins4_desc(n0, n1, n2, n3, last);
+    return make_uint4(n0, n1, n2, n3);
+}
+
+// returns {peak, valley}: mean of sqrt over the n largest / n smallest values of the band
+SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p, int lo, int count, int n) {
+    const int lane = threadIdx.x & 31;
+    const float* q = p + ppad(lo + lane);
+    const int mine = max((count - lane + 31) >> 5, 0);         // elements this lane owns
+    float2 r;
+    if (n == 1) {                                               // extremes of the band
+        unsigned mx = 0u, mn = 0xffffffffu;
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+        for (int i = 0; i < mine; ++i) {
+            const unsigned x = __float_as_uint(q[36 * i]);
+            mx = max(mx, x);
+            mn = min(mn, x);
+        }
+        r.x = sqrt_approx(__uint_as_float(__reduce_max_sync(kFull, mx)));
+        r.y = sqrt_approx(__uint_as_float(__reduce_min_sync(kFull, mn)));
+        return r;
+    }
+    const Sel4 t = track4(q, mine, count);
+    // both directions as "largest key first": top keys = bits, bottom keys = ~bits (0 = nothing)
+    unsigned a0 = t.a0, a1 = t.a1, a2 = t.a2, a3 = t.a3;
+    unsigned b0 = ~t.b0, b1 = ~t.b1, b2 = ~t.b2, b3 = ~t.b3;
+    int ra = n, rb = n;                                         // elements still to pop (warp uniform)
+    float sa = 0.0f, sb = 0.0f;
+    // One REDUX per step picks the warp-wide extreme among the lanes' heads; every lane holding that value pops it (ties
+    // pop together and are counted by value, so silent frames finish in one step).  Pops are selects, not branches.
+    //
+    // Untracked elements are <= their lane's 4th key <= T = max over lanes of the 4th keys, so the tracked keys above T
+    // are exactly the largest elements of the band.  If there are at least n of them (the common case), the n pops never
+    // leave the tracked quadruples and the lean loop needs no bookkeeping; otherwise (strongly clustered spectra) the
+    // full loop counts pops per lane and rebuilds the quadruple of a lane that runs dry.
+    bool lean = ((count + 31) >> 5) <= 4;
+    if (!lean) {
+        const unsigned ta = __reduce_max_sync(kFull, a3), tb = __reduce_max_sync(kFull, b3);
+        const int ca = (a0 > ta ? 1 : 0) + (a1 > ta ? 1 : 0) + (a2 > ta ? 1 : 0);
+        const int cb = (b0 > tb ? 1 : 0) + (b1 > tb ? 1 : 0) + (b2 > tb ? 1 : 0);
+        const unsigned cc = __reduce_add_sync(kFull, (unsigned)(ca | (cb << 16)));
+        lean = (int)(cc & 0xffffu) >= n && (int)(cc >> 16) >= n;
+    }
+    if (lean) {
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+        while (ra > 0 || rb > 0) {
+            if (ra > 0) {
+                const unsigned g = __reduce_max_sync(kFull, a0);
+                const bool own = (a0 == g);
+                const int c = min(__popc(__ballot_sync(kFull, own)), ra);
+                sa = __fmaf_rn((float)c, sqrt_approx(__uint_as_float(g)), sa);
+                ra -= c;
+                a0 = own ? a1 : a0; a1 = own ? a2 : a1; a2 = own ? a3 : a2; a3 = own ? 0u : a3;
+            }
+            if (rb > 0) {
+                const unsigned g = __reduce_max_sync(kFull, b0);
+                const bool own = (b0 == g);
+                const int c = min(__popc(__ballot_sync(kFull, own)), rb);
+                sb = __fmaf_rn((float)c, sqrt_approx(__uint_as_float(~g)), sb);
+                rb -= c;
+                b0 = own ? b1 : b0; b1 = own ? b2 : b1; b2 = own ? b3 : b2; b3 = own ? 0u : b3;
+            }
+        }
+    } else {
+        int ha = min(mine, 4), hb = ha;                         // tracked keys left
+        int pa = 0, pb = 0;                                     // elements popped by this lane
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+        while (ra > 0 || rb > 0) {
+            if (ra > 0) {
+                const unsigned g = __reduce_max_sync(kFull, a0);
+                const bool own = (a0 == g);
+                const int c = min(__popc(__ballot_sync(kFull, own)), ra);
+                sa = __fmaf_rn((float)c, sqrt_approx(__uint_as_float(g)), sa);
+                ra -= c;
+                a0 = own ? a1 : a0; a1 = own ? a2 : a1; a2 = own ? a3 : a2; a3 = own ? 0u : a3;
+                pa += own ? 1 : 0;
+                ha -= own ? 1 : 0;
+                if (__any_sync(kFull, ha == 0 && pa < mine) && ra > 0) {
+                    if (ha == 0 && pa < mine) {
+                        const uint4 v = refill4(q, mine, 0u, g, pa);
+                        a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w;
+                        ha = min(mine - pa, 4);
+                    }
+                }
+            }
+            if (rb > 0) {
+                const unsigned g = __reduce_max_sync(kFull, b0);
+                const bool own = (b0 == g);
+                const int c = min(__popc(__ballot_sync(kFull, own)), rb);
+                sb = __fmaf_rn((float)c, sqrt_approx(__uint_as_float(~g)), sb);
+                rb -= c;
+                b0 = own ? b1 : b0; b1 = own ? b2 : b1; b2 = own ? b3 : b2; b3 = own ? 0u : b3;
+                pb += own ? 1 : 0;
+                hb -= own ? 1 : 0;
+                if (__any_sync(kFull, hb == 0 && pb < mine) && rb > 0) {
+                    if (hb == 0 && pb < mine) {
+                        const uint4 v = refill4(q, mine, 0xffffffffu, g, pb);
+                        b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
+                        hb = min(mine - pb, 4);
+                    }
+                }
+            }
+        }
+    }
+    const float inv_n = 1.0f / (float)n;
+    r.x = sa * inv_n;
+    r.y = sb * inv_n;
+    return r;
+}
+
+// exact fallback for bands the register path does not cover (more than 1024 bins, or n > 32): bitwise search for the
+// n-th largest key over shared memory (ppad layout)
+SYG_DEVICE SYG_NOINLINE float band_select_slow36(const float* __restrict__ p, int lo, int count, int n, bool inv) {
+    const int lane = threadIdx.x & 31;
+    const unsigned flip = inv ? 0xffffffffu : 0u;
+    unsigned prefix = 0u;
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned trial = prefix | (1u << bit);
+        int cnt = 0;
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+        for (int i = lane; i < count; i += 32) cnt += ((__float_as_uint(p[ppad(lo + i)]) ^ flip) >= trial) ? 1 : 0;
+        cnt = __reduce_add_sync(kFull, cnt);
+        if (cnt >= n) prefix = trial;
+    }
+    float s_gt = 0.0f;
+    int c_gt = 0;
+#ifndef SYG_EMU
+#pragma unroll 1
+#endif
+    for (int i = lane; i < count; i += 32) {
+        const unsigned k = __float_as_uint(p[ppad(lo + i)]) ^ flip;
+        if (k > prefix) { s_gt += sqrt_approx(__uint_as_float(k ^ flip)); c_gt++; }
+    }
+    s_gt = warp_sum(s_gt);
+    c_gt = __reduce_add_sync(kFull, c_gt);
+    return s_gt + (float)(n - c_gt) * sqrt_approx(__uint_as_float(prefix ^ flip));
+}
+
+SYG_DEVICE SYG_INLINE void band_peak_valley_any(const float* __restrict__ p, int lo, int count, int n, float& peak, float& valley) {
+    if (count <= 0) { peak = valley = __uint_as_float(0x7fc00000u); return; }     // mean of nothing -> NaN (numpy)
+    if (n > count) n = count;
+    if (n < 1) n = 1;
+    const float2 r = band_peak_valley_stream(p, lo, count, n);
+    peak = r.x;
+    valley = r.y;
 }
 
 SYG_DEVICE SYG_NOINLINE void band_extremes_any(const float* __restrict__ p, int lo, int count, int n, unsigned* cand,

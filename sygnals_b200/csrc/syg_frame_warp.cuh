@@ -32,9 +32,9 @@ struct WarpTile {
     static constexpr int FW = 32 / G;                         // frames per warp
     static constexpr int R2 = TL::RLAST;                      // radix of pass 2
     static constexpr int ZS = M + (M >> LOG2E) + 1;           // float2 slots per frame
-    static constexpr int PS = padded_size(M + 1) + 4;         // floats per frame (+4: mel taps are read in groups of 4)
+    static constexpr int PS = ((M + 1) + 4 * ((M + 1) >> 5) + 4 + 3) / 4 * 4;   // floats per frame: 4 pad words per 32 bins (ppad), 16-byte multiple
     static constexpr int kWarps = NT / 32;
-    static constexpr int warp_floats = FW * (2 * ZS + PS) + 34;   // + 32 candidate slots and a counter for the contrast selection
+    static constexpr int warp_floats = (FW * (PS + 2 * ZS) + 3) / 4 * 4;        // P spectra first (float4 aligned), then the Z slices
     static constexpr size_t bytes = (size_t)kWarps * warp_floats * sizeof(float);
 };
 
@@ -83,14 +83,13 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     const int warp = tid >> 5, lane = tid & 31;
     const int f = lane / G, j = lane % G;
     float* const wbase = reinterpret_cast<float*>(smem_raw) + warp * WT::warp_floats;
-    float2* const zw = reinterpret_cast<float2*>(wbase);             // [FW][ZS]
-    float* const pww = wbase + FW * 2 * ZS;                           // [FW][PS]
-    float* const cand = pww + FW * PS;                                // [32]
+    float* const pww = wbase;                                         // [FW][PS]  |X|^2, ppad layout
+    float2* const zw = reinterpret_cast<float2*>(wbase + FW * PS);   // [FW][ZS]
     float2* const zs = zw + f * ZS;
     float* const pf = pww + f * PS;
 
-    // pad slots / guard words of the power spectra are read (with zero weight) by the mel sweep: keep them finite
-    for (int i = lane; i < FW * PS + 34; i += 32) pww[i] = 0.0f;
+    // pad words of the power spectra are read (with zero weight) by the mel sweep: keep them finite
+    for (int i = lane; i < FW * PS; i += 32) pww[i] = 0.0f;
     __syncwarp();
 
     const long long n_tasks = (a.n_frames + FW - 1) / FW;
@@ -217,8 +216,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             float xkr, xki, xmr, xmi;
             real_split(zk.x, zk.y, zm.x, zm.y, w.x, w.y, xkr, xki, xmr, xmi);
             const int k2 = M - k;
-            pf[padi(k)] = __fmaf_rn(xkr, xkr, xki * xki);
-            if (k2 != k) pf[padi(k2)] = __fmaf_rn(xmr, xmr, xmi * xmi);
+            pf[ppad(k)] = __fmaf_rn(xkr, xkr, xki * xki);
+            if (k2 != k) pf[ppad(k2)] = __fmaf_rn(xmr, xmr, xmi * xmi);
         }
         __syncwarp();
 
@@ -255,59 +254,92 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         // ---------------- per-frame spectral statistics (lane j owns bins [j*E, j*E+E), last lane also bin M) ----------------
         if (a.mask & syg::FB_SPECSTATS) {
             const int k0 = j * E;
-            const float* pb = pf + padi(k0);                            // bin k0 + i at pb[i] (i < E <= 32)
-            double sp = 0.0, sp1 = 0.0;
-            float sm = 0.0f, skm = 0.0f, slog = 0.0f, sm1 = 0.0f, skm1 = 0.0f;
-            float vmax = -1.0f;
-            int imax = 0;
-            const float kf0 = (float)k0;
-            SYG_UNROLL
-            for (int i = 0; i < E; ++i) {
-                const float p = pb[i];
-                const float mg = sqrt_approx(p);
-                if (i & 1) { sp1 += (double)p; sm1 += mg; skm1 = __fmaf_rn(mg, kf0 + (float)i, skm1); }
-                else { sp += (double)p; sm += mg; skm = __fmaf_rn(mg, kf0 + (float)i, skm); }
-                if (EXTRA) {
-                    if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p) + 2.220446049250313e-16f);
-                    if (p > vmax) { vmax = p; imax = k0 + i; }
+            float p[E];
+            {
+                const float4* pb4 = reinterpret_cast<const float4*>(pf + ppad(k0));   // E is a multiple of 4 and <= 32: one block
+                SYG_UNROLL
+                for (int i = 0; i < E / 4; ++i) {
+                    const float4 v = pb4[i];
+                    p[4 * i] = v.x; p[4 * i + 1] = v.y; p[4 * i + 2] = v.z; p[4 * i + 3] = v.w;
                 }
             }
-            sp += sp1; sm += sm1; skm += skm1;
-            const float p_ny = pf[padi(M)];
+            float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sm[2] = {0.0f, 0.0f}, skm[2] = {0.0f, 0.0f};
+            float slog = 0.0f, vmax = -1.0f;
+            int imax = 0;
+            SYG_UNROLL
+            for (int i = 0; i < E; ++i) {
+                const float mg = sqrt_approx(p[i]);
+                sp[i & 3] += p[i];
+                sm[i & 1] += mg;
+                skm[i & 1] = __fmaf_rn(mg, (float)i, skm[i & 1]);
+                if (EXTRA) {
+                    if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p[i]) + 2.220446049250313e-16f);
+                    if (p[i] > vmax) { vmax = p[i]; imax = k0 + i; }
+                }
+            }
+            float lsp = (sp[0] + sp[1]) + (sp[2] + sp[3]);
+            float lsm = sm[0] + sm[1];
+            float lskm = __fmaf_rn(lsm, (float)k0, skm[0] + skm[1]);     // sum (k0 + i) mag_i
+            const float p_ny = pf[ppad(M)];
             if (j == G - 1) {                                            // bin M (Nyquist)
                 const float mg = sqrt_approx(p_ny);
-                sp += (double)p_ny;
-                sm += mg;
-                skm = __fmaf_rn(mg, (float)M, skm);
+                lsp += p_ny;
+                lsm += mg;
+                lskm = __fmaf_rn(mg, (float)M, lskm);
                 if (EXTRA) {
                     if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p_ny) + 2.220446049250313e-16f);
                     if (p_ny > vmax) { vmax = p_ny; imax = M; }
                 }
             }
             const int nk = E + ((j == G - 1) ? 1 : 0);
-            const double incl = lanes_scan_incl<G>(sp, j);
+            // lane sums are FP32 (pairwise, <= 33 terms); the running sum across lanes is FP64 (reference: float64 cumsum)
+            const double incl = lanes_scan_incl<G>((double)lsp, j);
             const double total_p = __shfl_sync(kFull, incl, G - 1, G);
-            double prev = __shfl_up_sync(kFull, incl, 1, G);
-            if (j == 0) prev = -1.0;
-            const float tm = lanes_sum<G>(sm);
-            const float tkm = lanes_sum<G>(skm);
+            const float tm = lanes_sum<G>(lsm);
+            const float tkm = lanes_sum<G>(lskm);
             double centroid_hz = 0.0;
             if ((double)tm >= kEps64) centroid_hz = a.bin_hz * ((double)tkm / (double)tm);
             if (a.row_centroid >= 0 && j == 0 && valid) orow[(long long)a.row_centroid * a.T] = (float)centroid_hz;
             if (a.row_rolloff >= 0) {
-                if (total_p < kEps64) {
-                    if (j == 0 && valid) orow[(long long)a.row_rolloff * a.T] = (float)(a.bin_hz * (double)M);
-                } else {
-                    const double thr = a.roll_percent * total_p;
-                    if (incl >= thr && prev < thr) {                   // exactly one lane of the group
-                        double c = (j == 0) ? 0.0 : prev;
-                        int bin = k0 + nk - 1;
-                        for (int i = 0; i < nk; ++i) {
-                            c += (double)pf[padi(k0 + i)];
-                            if (c >= thr) { bin = k0 + i; break; }
-                        }
-                        if (valid) orow[(long long)a.row_rolloff * a.T] = (float)(a.bin_hz * (double)bin);
-                    }
+                // first bin whose cumulative power reaches roll_percent * total (frequency_domain.py:334-346)
+                const double thr = a.roll_percent * total_p;
+                const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << (f * G));
+                const unsigned hit = __ballot_sync(kFull, incl >= thr) & gmask;
+                const int L = hit ? (__ffs((int)hit) - 1 - f * G) : (G - 1);          // crossing lane of this frame's group
+                const double prevL = __shfl_sync(kFull, incl - (double)lsp, L, G);
+                const float thrl = (float)(thr - prevL);
+                // the group's lanes scan lane L's E bins together: R consecutive bins each
+                constexpr int R = (E + G - 1) / G;
+                const int kL = L * E;
+                float v[R], s = 0.0f;
+                SYG_UNROLL
+                for (int r = 0; r < R; ++r) {
+                    const int q = j * R + r;
+                    v[r] = (q < E) ? pf[ppad(kL + q)] : 0.0f;
+                    s += v[r];
+                }
+                float inc = s;
+                SYG_UNROLL
+                for (int o = 1; o < G; o <<= 1) {
+                    const float nb_ = __shfl_up_sync(kFull, inc, o, G);
+                    if (j >= o) inc += nb_;
+                }
+                float c = inc - s;
+                int pos = -1;
+                SYG_UNROLL
+                for (int r = 0; r < R; ++r) {
+                    c += v[r];
+                    if (pos < 0 && j * R + r < E && c >= thrl) pos = j * R + r;
+                }
+                const unsigned found = __ballot_sync(kFull, pos >= 0) & gmask;
+                const int src = found ? (__ffs((int)found) - 1 - f * G) : 0;
+                const int posw = __shfl_sync(kFull, pos, src, G);
+                if (j == 0 && valid) {
+                    int bin;
+                    if (total_p < kEps64) bin = M;                                      // silent frame -> freqs[-1]
+                    else if (found) bin = kL + posw;
+                    else bin = (L == G - 1) ? M : kL + E - 1;                           // only the lane's last element is left
+                    orow[(long long)a.row_rolloff * a.T] = (float)(a.bin_hz * (double)bin);
                 }
             }
             if (EXTRA) {
@@ -325,10 +357,15 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 }
                 if (a.row_bandwidth >= 0) {
                     double sb = 0.0;
-                    for (int i = 0; i < nk; ++i) {
-                        const double mg = (double)sqrtf(pf[padi(k0 + i)]);
+                    SYG_UNROLL
+                    for (int i = 0; i < E; ++i) {
+                        const double mg = (double)sqrtf(p[i]);
                         const double d = a.bin_hz * (double)(k0 + i) - centroid_hz;
                         sb += mg * d * d;
+                    }
+                    if (nk > E) {
+                        const double d = a.bin_hz * (double)M - centroid_hz;
+                        sb += (double)sqrtf(p_ny) * d * d;
                     }
                     const double tb = lanes_sum<G>(sb);
                     if (j == 0 && valid) orow[(long long)a.row_bandwidth * a.T] = ((double)tm < kEps64) ? 0.0f : (float)sqrt(tb / (double)tm);
@@ -343,48 +380,51 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         }
 
         if (SYNCP) __syncthreads();
-        // ---------------- mel energies: lanes sweep (frame, slot) pairs; slots are filters sorted by span ----------------
+        // ---------------- mel energies: one filter per lane, 32 filters of similar span per sweep (syg_plan.h) ----------------
         if (a.mask & syg::FB_MFCC) {
-            float fmx[FW];
-            SYG_UNROLL
-            for (int ff = 0; ff < FW; ++ff) fmx[ff] = 0.0f;
-            const int ntask = FW * a.n_mels;
-            for (int base = 0; base < ntask; base += 32) {
-                const int mt = base + lane;
-                if (mt < ntask) {
-                    const int ff = (FW == 1) ? 0 : mt / a.n_mels;
-                    const int slot = mt - ff * a.n_mels;
-                    const long long gff = task * FW + ff;
-                    if (gff < a.n_frames) {
-                        const int4 d = __ldg(&a.mel_slots[slot]);       // {filter, padded start, taps, offset}
-                        const float4* wv = reinterpret_cast<const float4*>(a.mel_pw + d.w);
-                        const float* pp = pww + ff * PS + d.y;
-                        float acc = 0.0f;
-                        if (a.mel_power_is_2) {
-                            float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                            for (int i = 0; i < d.z; i += 4) {
-                                const float4 w = __ldg(wv + (i >> 2));
-                                acc = __fmaf_rn(w.x, pp[i], acc);
-                                a1 = __fmaf_rn(w.y, pp[i + 1], a1);
-                                a2 = __fmaf_rn(w.z, pp[i + 2], a2);
-                                a3 = __fmaf_rn(w.w, pp[i + 3], a3);
-                            }
-                            acc = (acc + a1) + (a2 + a3);
-                        } else {
-                            for (int i = 0; i < d.z; ++i)
-                                acc = __fmaf_rn(__ldg(a.mel_pw + d.w + i), powf(pp[i], a.mel_half_power), acc);
+            const float4* const mw4 = reinterpret_cast<const float4*>(a.mel_pw);
+            for (int ff = 0; ff < FW; ++ff) {
+                const long long gff = task * FW + ff;
+                if (gff >= a.n_frames) break;
+                const float* pfr = pww + ff * PS;
+                float fmx = 0.0f;
+                for (int base = 0; base < a.n_mels; base += 32) {
+                    const int slot = min(base + lane, a.n_mels - 1);
+                    const int4 d = __ldg(&a.mel_slots[slot]);           // {filter, first padded word, steps, tap offset}: steps/offset are warp uniform
+                    const float4* wv = mw4 + d.w + lane;
+                    const float4* pp4 = reinterpret_cast<const float4*>(pfr + d.y);
+                    float acc = 0.0f;
+                    if (a.mel_power_is_2) {
+                        float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#ifndef SYG_EMU
+#pragma unroll 4
+#endif
+                        for (int i = 0; i < d.z; ++i) {
+                            const float4 w = __ldg(wv + 32 * i);
+                            const float4 q = pp4[i];
+                            acc = __fmaf_rn(w.x, q.x, acc);
+                            a1 = __fmaf_rn(w.y, q.y, a1);
+                            a2 = __fmaf_rn(w.z, q.z, a2);
+                            a3 = __fmaf_rn(w.w, q.w, a3);
                         }
+                        acc = (acc + a1) + (a2 + a3);
+                    } else {
+                        for (int i = 0; i < d.z; ++i) {
+                            const float4 w = __ldg(wv + 32 * i);
+                            const float4 q = pp4[i];
+                            acc = __fmaf_rn(w.x, powf(q.x, a.mel_half_power), acc);
+                            acc = __fmaf_rn(w.y, powf(q.y, a.mel_half_power), acc);
+                            acc = __fmaf_rn(w.z, powf(q.z, a.mel_half_power), acc);
+                            acc = __fmaf_rn(w.w, powf(q.w, a.mel_half_power), acc);
+                        }
+                    }
+                    if (base + lane < a.n_mels) {
                         a.melws[gff * a.n_mels + d.x] = acc;
-                        SYG_UNROLL
-                        for (int q = 0; q < FW; ++q) if (q == ff) fmx[q] = fmaxf(fmx[q], acc);
+                        fmx = fmaxf(fmx, acc);
                     }
                 }
-            }
-            SYG_UNROLL
-            for (int ff = 0; ff < FW; ++ff) {
-                const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fmx[ff], 0.0f)));
-                const long long gff = task * FW + ff;
-                if (lane == 0 && gff < a.n_frames && mx != 0u) atomicMax(&a.unit_max[(gff / a.T) * 4 + 0], mx);
+                const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fmx, 0.0f)));
+                if (lane == 0 && mx != 0u) atomicMax(&a.unit_max[(gff / a.T) * 4 + 0], mx);
             }
         }
 
@@ -398,7 +438,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 float pmx = 0.0f, vmx = 0.0f;
                 for (int bd = 0; bd < a.nb; ++bd) {
                     float peak, valley;
-                    band_extremes_any(pp, a.band_lo[bd], a.band_cnt[bd], a.band_n[bd], reinterpret_cast<unsigned*>(cand), peak, valley);
+                    band_peak_valley_any(pp, a.band_lo[bd], a.band_cnt[bd], a.band_n[bd], peak, valley);
                     if (lane == 0) {
                         a.cws[gff * (2 * a.nb) + bd] = peak;
                         a.cws[gff * (2 * a.nb) + a.nb + bd] = valley;

@@ -127,31 +127,45 @@ inline bool build_mel(double sr, int n_fft, int n_mels, double fmin, double fmax
 // weight at every pad position) and padded to a multiple of 4 taps.  desc = {filter m, padded start, taps, offset}.
 struct MelSlots { std::vector<int> desc; std::vector<float> w; };
 
-inline void build_mel_slots(const MelTable& t, MelSlots& s) {
+inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
+    // Slots live in the warp kernel's padded spectrum space: ppad(k) = k + 4 * (k / 32) (4 pad words after every 32 bins).
+    // Filters are sorted by span and taken 32 at a time (one per lane); every slot of a group spans the same number L of
+    // float4 steps (the group's longest filter, zero weights elsewhere) so the sweep has a warp-uniform trip count, and
+    // the group's taps are interleaved [step][lane] so one LDG.128 per step is a fully coalesced 512-byte read.
+    //   desc[slot] = {filter, first padded word (multiple of 4), L, offset of the group's taps in float4 units}
+    auto ppad = [](int k) { return k + ((k >> 5) << 2); };
+    const int ps_words = ((n_bins + 4 * (n_bins >> 5) + 4 + 3) / 4) * 4;      // = WarpTile::PS
     std::vector<int> order(t.n_mels);
     for (int i = 0; i < t.n_mels; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return t.len[a] > t.len[b]; });
-    s.desc.clear(); s.w.clear();
-    for (int m : order) {
-        int pst = 0, ln4 = 0;
-        const int off = (int)s.w.size();
-        if (t.len[m] > 0) {
-            const int k0 = t.start[m], k1 = t.start[m] + t.len[m] - 1;
-            pst = k0 + (k0 >> 5);
-            const int pend = k1 + (k1 >> 5);
-            ln4 = ((pend - pst + 1) + 3) / 4 * 4;
-            for (int p = pst; p < pst + ln4; ++p) {
-                float wv = 0.0f;
-                if (p <= pend && (p % 33) != 32) {
-                    const int k = 32 * (p / 33) + (p % 33);
-                    wv = t.w[t.off[m] + (k - k0)];
-                }
-                s.w.push_back(wv);
-            }
+    s.desc.assign((size_t)t.n_mels * 4, 0);
+    s.w.clear();
+    for (int g0 = 0; g0 < t.n_mels; g0 += 32) {
+        const int gn = std::min(32, t.n_mels - g0);
+        int L = 1;
+        std::vector<int> pst(gn, 0);
+        for (int j = 0; j < gn; ++j) {
+            const int m = order[g0 + j];
+            if (t.len[m] <= 0) continue;
+            pst[j] = ppad(t.start[m]) & ~3;
+            L = std::max(L, (ppad(t.start[m] + t.len[m] - 1) - pst[j] + 1 + 3) / 4);
         }
-        s.desc.push_back(m); s.desc.push_back(pst); s.desc.push_back(ln4); s.desc.push_back(off);
+        for (int j = 0; j < gn; ++j) pst[j] = std::max(0, std::min(pst[j], ps_words - 4 * L));   // keep the sweep inside the buffer
+        const int goff4 = (int)(s.w.size() / 4);
+        s.w.resize(s.w.size() + (size_t)L * 32 * 4, 0.0f);
+        for (int j = 0; j < gn; ++j) {
+            const int m = order[g0 + j];
+            for (int i = 0; i < 4 * L; ++i) {
+                const int p = pst[j] + i, blk = p / 36, r = p % 36, k = 32 * blk + r;
+                float wv = 0.0f;
+                if (t.len[m] > 0 && r < 32 && k >= t.start[m] && k < t.start[m] + t.len[m]) wv = t.w[t.off[m] + (k - t.start[m])];
+                s.w[((size_t)goff4 + (size_t)(i / 4) * 32 + j) * 4 + (i % 4)] = wv;
+            }
+            int* d = &s.desc[(size_t)(g0 + j) * 4];
+            d[0] = m; d[1] = pst[j]; d[2] = L; d[3] = goff4;
+        }
     }
-    if (s.w.empty()) s.w.push_back(0.0f);
+    if (s.w.empty()) s.w.assign(4, 0.0f);
 }
 
 // rows [n_out][n_mels] of the DCT scipy.fftpack.dct(x, type, norm) restricted to the first n_out outputs,

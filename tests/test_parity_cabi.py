@@ -194,6 +194,34 @@ def test_features_vs_oracle(eng, sr, fl, hop, n, features, fp):
     check_rows(names, out[0], ref, bin_hz=sr / fl)
 
 
+@pytest.mark.parametrize("case", ["comb32", "comb32_low", "two_level", "quantile10"])
+def test_contrast_selection_stress(eng, case):
+    """Spectral-contrast selection when the band's largest bins share a lane of the lane-striped layout (tones 32 bins
+    apart), when many bins tie, and with a large quantile (n up to 32 per band)."""
+    sr, fl, hop, n = 44100, 2048, 512, 6000
+    t = np.arange(n) / sr
+    rng = np.random.default_rng(5)
+    fp = None
+    if case in ("comb32", "comb32_low"):
+        k0 = 600 if case == "comb32" else 300                      # bins k0 + 32 i: one lane of the top / second band
+        y = 1e-2 * rng.standard_normal(n)
+        for i in range(13):
+            y += (0.05 + 0.002 * i) * np.sin(2 * np.pi * (k0 + 32 * i) * sr / fl * t + i)
+    elif case == "two_level":
+        y = np.where((np.arange(n) // 7) % 2 == 0, 0.25, -0.25) + 1e-4 * rng.standard_normal(n)
+    else:
+        y = 0.3 * rng.standard_normal(n)
+        fp = {"spectral_contrast": {"quantile": 0.1, "n_bands": 4, "fmin": 400.0}}
+    y = y.astype(np.float32)
+    feats = ["spectral_contrast"]
+    names, ref = oracle_rows(y, sr, feats, fl, hop, fp)
+    p = _ffi.make_params(eng.lib, sr, feats, fl, hop, feature_params=fp)
+    out = eng.features_host(y, eng.units_clips(1, n), p)
+    S = np.abs(orc.compute_stft(y.astype(np.float64), n_fft=fl, hop_length=hop))
+    ok = (S.min(axis=0) >= 1e-5 * S.max(axis=0))
+    check_rows(names, out[0], ref, bin_hz=sr / fl, contrast_ok=ok)
+
+
 @pytest.mark.parametrize("kind", synth.EDGE_KINDS)
 def test_edge_clips_vs_oracle(eng, kind):
     sr, fl, hop, n = 22050, 1024, 256, 6000
