@@ -309,8 +309,8 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         a.n_mels = p->n_mels;
         a.mel_power_is_2 = (p->power == 2.0);
         a.mel_half_power = (float)(0.5 * p->power);
-        std::string dk = keyf("dct:%d:%d:%d:%d:%.9g", p->n_mfcc, p->n_mels, p->dct_type, p->dct_ortho, (double)p->lifter);
-        std::vector<float> dct;
+        std::string dk = keyf("dct64:%d:%d:%d:%d:%.9g", p->n_mfcc, p->n_mels, p->dct_type, p->dct_ortho, (double)p->lifter);
+        std::vector<double> dct;
         if (!ctx->tables.count(dk)) {
             std::string err;
             if (!sygplan::build_dct(p->n_mfcc, p->n_mels, p->dct_type, p->dct_ortho != 0, (double)p->lifter, p->n_mfcc, dct, err))
@@ -371,7 +371,7 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
         f.unit_max = a.unit_max;
         f.out = out;
         const int gx = (pl.T + sygdev::kFinTT - 1) / sygdev::kFinTT;
-        const size_t smem = (size_t)sygdev::kFinTT * (f.n_mels + 1) * sizeof(float);
+        const size_t smem = (size_t)sygdev::kFinTT * (f.n_mels + 1) * sizeof(double);
         for (long long u0 = 0; u0 < g.n_units; u0 += 65535) {       // gridDim.y limit
             syg::FinalizeArgs fc = f;
             fc.n_units = std::min<long long>(65535, g.n_units - u0);

@@ -747,26 +747,22 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
         lean = (int)(cc & 0xffffu) >= n && (int)(cc >> 16) >= n;
     }
     if (lean) {
+        // one element per step and direction (the lowest lane holding the extreme pops), both directions in one
+        // straight-line body: two independent REDUX chains for the scheduler to interleave
+        const unsigned lt = (1u << lane) - 1u;
 #ifndef SYG_EMU
 #pragma unroll 1
 #endif
-        while (ra > 0 || rb > 0) {
-            if (ra > 0) {
-                const unsigned g = __reduce_max_sync(kFull, a0);
-                const bool own = (a0 == g);
-                const int c = min(__popc(__ballot_sync(kFull, own)), ra);
-                sa = __fmaf_rn((float)c, sqrt_approx(__uint_as_float(g)), sa);
-                ra -= c;
-                a0 = own ? a1 : a0; a1 = own ? a2 : a1; a2 = own ? a3 : a2; a3 = own ? 0u : a3;
-            }
-            if (rb > 0) {
-                const unsigned g = __reduce_max_sync(kFull, b0);
-                const bool own = (b0 == g);
-                const int c = min(__popc(__ballot_sync(kFull, own)), rb);
-                sb = __fmaf_rn((float)c, sqrt_approx(__uint_as_float(~g)), sb);
-                rb -= c;
-                b0 = own ? b1 : b0; b1 = own ? b2 : b1; b2 = own ? b3 : b2; b3 = own ? 0u : b3;
-            }
+        for (int it = 0; it < n; ++it) {
+            const unsigned ga = __reduce_max_sync(kFull, a0);
+            const unsigned gb = __reduce_max_sync(kFull, b0);
+            const bool ea = (a0 == ga), eb = (b0 == gb);
+            const unsigned ma = __ballot_sync(kFull, ea), mb = __ballot_sync(kFull, eb);
+            const bool oa = ea && (ma & lt) == 0u, ob = eb && (mb & lt) == 0u;
+            sa += sqrt_approx(__uint_as_float(ga));
+            sb += sqrt_approx(__uint_as_float(~gb));
+            a0 = oa ? a1 : a0; a1 = oa ? a2 : a1; a2 = oa ? a3 : a2; a3 = oa ? 0u : a3;
+            b0 = ob ? b1 : b0; b1 = ob ? b2 : b1; b2 = ob ? b3 : b2; b3 = ob ? 0u : b3;
         }
     } else {
         int ha = min(mine, 4), hb = ha;                         // tracked keys left

@@ -16,7 +16,6 @@ namespace sygdev {
 
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeArgs a) {
     SYG_DYN_SMEM(smem_raw);
-    float* const sdb = reinterpret_cast<float*>(smem_raw);   // [kFinTT][n_mels + 1]
     const int tid = threadIdx.x;
     const long long u = blockIdx.y;
     const int t0 = blockIdx.x * kFinTT;
@@ -25,6 +24,9 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeA
     float* const obase = a.out + u * (long long)a.n_rows * a.T;
 
     if (a.row_mfcc >= 0) {
+        // S_db tile in float64: the DCT accumulates in FP64 (|sum| reaches 80*sqrt(n_mels) ~ 905 and the parity bar is 1e-3
+        // absolute); converting each S_db value once here (not once per DCT row) keeps the conversion pipe out of the way
+        double* const sdb = reinterpret_cast<double*>(smem_raw);            // [kFinTT][n_mels + 1]
         const int ld = a.n_mels + 1;
         const float ref = fmaxf(a.amin, __uint_as_float(um[0]));
         const float ref_db = 10.0f * log10f(ref);
@@ -35,18 +37,25 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeA
             const int tt = i / a.n_mels, m = i - tt * a.n_mels;
             const float e = a.melws[((u * a.T) + t0 + tt) * a.n_mels + m];
             float db = 10.0f * log10f(fmaxf(a.amin, e)) - ref_db;
-            sdb[tt * ld + m] = fmaxf(db, floor_db);
+            sdb[tt * ld + m] = (double)fmaxf(db, floor_db);
         }
         __syncthreads();
         for (int i = tid; i < a.n_mfcc * kFinTT; i += kThreads) {
             const int c = i / kFinTT, tt = i - c * kFinTT;
             if (tt < nt) {
-                const float* d = a.dct + c * a.n_mels;
-                const float* s = sdb + tt * ld;
-                // FP64 accumulation: |sum| reaches 80*sqrt(n_mels) (~905) and the parity bar is 1e-3 absolute
-                double acc = 0.0;
-                for (int m = 0; m < a.n_mels; ++m) acc = fma((double)__ldg(&d[m]), (double)s[m], acc);
-                obase[(long long)(a.row_mfcc + c) * a.T + t0 + tt] = (float)acc;
+                const double* d = a.dct + c * a.n_mels;
+                const double* s = sdb + tt * ld;
+                // four independent chains: a single dependent DFMA chain of n_mels links is latency bound
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+                int m = 0;
+                for (; m + 4 <= a.n_mels; m += 4) {
+                    acc0 = fma(__ldg(&d[m]), s[m], acc0);
+                    acc1 = fma(__ldg(&d[m + 1]), s[m + 1], acc1);
+                    acc2 = fma(__ldg(&d[m + 2]), s[m + 2], acc2);
+                    acc3 = fma(__ldg(&d[m + 3]), s[m + 3], acc3);
+                }
+                for (; m < a.n_mels; ++m) acc0 = fma(__ldg(&d[m]), s[m], acc0);
+                obase[(long long)(a.row_mfcc + c) * a.T + t0 + tt] = (float)((acc0 + acc1) + (acc2 + acc3));
             }
         }
     }

@@ -32,9 +32,12 @@ struct WarpTile {
     static constexpr int FW = 32 / G;                         // frames per warp
     static constexpr int R2 = TL::RLAST;                      // radix of pass 2
     static constexpr int ZS = M + (M >> LOG2E) + 1;           // float2 slots per frame
-    static constexpr int PS = ((M + 1) + 4 * ((M + 1) >> 5) + 4 + 3) / 4 * 4;   // floats per frame: 4 pad words per 32 bins (ppad), 16-byte multiple
+    static constexpr int PS = ((M + 1) + 4 * ((M + 1) >> 5) + 16 + 3) / 4 * 4;  // floats per frame: 4 pad words per 32 bins (ppad) + 16 words of sweep slack
     static constexpr int kWarps = NT / 32;
-    static constexpr int warp_floats = (FW * (PS + 2 * ZS) + 3) / 4 * 4;        // P spectra first (float4 aligned), then the Z slices
+    // one region per frame, used twice: as the Z exchange buffer of the FFT, then (Z is dead once the real split has pulled
+    // its pairs into registers) as the |X|^2 spectrum.  Halves the shared memory per warp, which the SM hands to L1.
+    static constexpr int RS = ((2 * ZS > PS ? 2 * ZS : PS) + 3) / 4 * 4;
+    static constexpr int warp_floats = FW * RS;
     static constexpr size_t bytes = (size_t)kWarps * warp_floats * sizeof(float);
 };
 
@@ -72,6 +75,10 @@ SYG_DEVICE SYG_INLINE double lanes_scan_incl(double v, int gl) {
 // SYNCP: CTA barriers at the phase boundaries.  Not needed for correctness (warps own disjoint shared-memory slices);
 // they keep the warps of a CTA inside the same code region, which is what the instruction caches want: the per-frame
 // code is ~6000 straight-line instructions, several times the L1.5 instruction cache.
+SYG_DEVICE SYG_INLINE long long unit_of(long long frame, int T, bool small) {
+    return small ? (long long)((unsigned)frame / (unsigned)T) : frame / T;
+}
+
 template <class TL, bool EXTRA, int NT, int MINB, bool SYNCP>
 __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameArgs a) {
     using WT = WarpTile<TL, NT>;
@@ -83,22 +90,22 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     const int warp = tid >> 5, lane = tid & 31;
     const int f = lane / G, j = lane % G;
     float* const wbase = reinterpret_cast<float*>(smem_raw) + warp * WT::warp_floats;
-    float* const pww = wbase;                                         // [FW][PS]  |X|^2, ppad layout
-    float2* const zw = reinterpret_cast<float2*>(wbase + FW * PS);   // [FW][ZS]
-    float2* const zs = zw + f * ZS;
-    float* const pf = pww + f * PS;
+    float* const pww = wbase;                                         // [FW][RS]  Z (float2, zpad layout), later |X|^2 (ppad layout)
+    float2* const zs = reinterpret_cast<float2*>(wbase + f * WT::RS);
+    float* const pf = wbase + f * WT::RS;
 
-    // pad words of the power spectra are read (with zero weight) by the mel sweep: keep them finite
-    for (int i = lane; i < FW * PS; i += 32) pww[i] = 0.0f;
+    // pad / slack words of the spectra are read (with zero weight) by the mel sweep: they must never hold NaN patterns
+    for (int i = lane; i < WT::warp_floats; i += 32) wbase[i] = 0.0f;
     __syncwarp();
 
     const long long n_tasks = (a.n_frames + FW - 1) / FW;
+    const bool small = a.n_frames <= 0x7fffffffLL;                   // 32-bit index arithmetic (a 64-bit division costs ~100 instructions)
     // all warps of the CTA run the same number of iterations (tasks past the end are processed as empty frames)
     for (long long task0 = (long long)blockIdx.x * WT::kWarps; task0 < n_tasks; task0 += (long long)gridDim.x * WT::kWarps) {
         const long long task = task0 + warp;
         const long long gf = task * FW + f;
         const bool valid = gf < a.n_frames;
-        const long long u = valid ? gf / a.T : 0;
+        const long long u = valid ? unit_of(gf, a.T, small) : 0;
         const int t = valid ? (int)(gf - u * a.T) : 0;
         UnitRef ur = unit_ref(a.g, u);
         if (!valid) ur.valid = 0;
@@ -205,19 +212,27 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         __syncwarp();
 
         if (SYNCP) __syncthreads();
-        // ---------------- real split -> |X[k]|^2 ----------------
-        SYG_UNROLL
-        for (int i = 0; i <= E / 2; ++i) {
-            const int k = j + i * G;
-            if (i == E / 2 && j != 0) break;
-            const int km = (M - k) & (M - 1);
-            const float2 zk = zs[zpad<LE>(k)], zm = zs[zpad<LE>(km)];
-            const float2 w = __ldg(&a.tws[k]);
-            float xkr, xki, xmr, xmi;
-            real_split(zk.x, zk.y, zm.x, zm.y, w.x, w.y, xkr, xki, xmr, xmi);
-            const int k2 = M - k;
-            pf[ppad(k)] = __fmaf_rn(xkr, xkr, xki * xki);
-            if (k2 != k) pf[ppad(k2)] = __fmaf_rn(xmr, xmr, xmi * xmi);
+        // ---------------- real split -> |X[k]|^2 (overwrites the Z region: all pairs are pulled into registers first) ----------------
+        {
+            float2 zk[E / 2 + 1], zm[E / 2 + 1];
+            SYG_UNROLL
+            for (int i = 0; i <= E / 2; ++i) {
+                const int k = j + i * G;
+                zk[i] = zs[zpad<LE>(k)];
+                zm[i] = zs[zpad<LE>((M - k) & (M - 1))];
+            }
+            __syncwarp();
+            SYG_UNROLL
+            for (int i = 0; i <= E / 2; ++i) {
+                const int k = j + i * G;
+                if (i == E / 2 && j != 0) break;
+                const float2 w = __ldg(&a.tws[k]);
+                float xkr, xki, xmr, xmi;
+                real_split(zk[i].x, zk[i].y, zm[i].x, zm[i].y, w.x, w.y, xkr, xki, xmr, xmi);
+                const int k2 = M - k;
+                pf[ppad(k)] = __fmaf_rn(xkr, xkr, xki * xki);
+                if (k2 != k) pf[ppad(k2)] = __fmaf_rn(xmr, xmr, xmi * xmi);
+            }
         }
         __syncwarp();
 
@@ -386,7 +401,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             for (int ff = 0; ff < FW; ++ff) {
                 const long long gff = task * FW + ff;
                 if (gff >= a.n_frames) break;
-                const float* pfr = pww + ff * PS;
+                const float* pfr = pww + ff * WT::RS;
                 float fmx = 0.0f;
                 for (int base = 0; base < a.n_mels; base += 32) {
                     const int slot = min(base + lane, a.n_mels - 1);
@@ -397,15 +412,18 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     if (a.mel_power_is_2) {
                         float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #ifndef SYG_EMU
-#pragma unroll 4
+#pragma unroll 1
 #endif
-                        for (int i = 0; i < d.z; ++i) {
-                            const float4 w = __ldg(wv + 32 * i);
-                            const float4 q = pp4[i];
-                            acc = __fmaf_rn(w.x, q.x, acc);
-                            a1 = __fmaf_rn(w.y, q.y, a1);
-                            a2 = __fmaf_rn(w.z, q.z, a2);
-                            a3 = __fmaf_rn(w.w, q.w, a3);
+                        for (int i = 0; i < d.z; i += 4) {              // steps come in multiples of four (syg_plan.h)
+                            SYG_UNROLL
+                            for (int c = 0; c < 4; ++c) {
+                                const float4 w = __ldg(wv + 32 * (i + c));
+                                const float4 q = pp4[i + c];
+                                acc = __fmaf_rn(w.x, q.x, acc);
+                                a1 = __fmaf_rn(w.y, q.y, a1);
+                                a2 = __fmaf_rn(w.z, q.z, a2);
+                                a3 = __fmaf_rn(w.w, q.w, a3);
+                            }
                         }
                         acc = (acc + a1) + (a2 + a3);
                     } else {
@@ -424,7 +442,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     }
                 }
                 const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fmx, 0.0f)));
-                if (lane == 0 && mx != 0u) atomicMax(&a.unit_max[(gff / a.T) * 4 + 0], mx);
+                if (lane == 0 && mx != 0u) atomicMax(&a.unit_max[unit_of(gff, a.T, small) * 4 + 0], mx);
             }
         }
 
@@ -434,7 +452,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             for (int ff = 0; ff < FW; ++ff) {
                 const long long gff = task * FW + ff;
                 if (gff >= a.n_frames) break;
-                const float* pp = pww + ff * PS;
+                const float* pp = pww + ff * WT::RS;
                 float pmx = 0.0f, vmx = 0.0f;
                 for (int bd = 0; bd < a.nb; ++bd) {
                     float peak, valley;
@@ -447,7 +465,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     if (valley == valley) vmx = fmaxf(vmx, valley);
                 }
                 if (lane == 0) {
-                    unsigned* um = a.unit_max + (gff / a.T) * 4;
+                    unsigned* um = a.unit_max + unit_of(gff, a.T, small) * 4;
                     if (pmx > 0.0f) atomicMax(&um[1], __float_as_uint(pmx));
                     if (vmx > 0.0f) atomicMax(&um[2], __float_as_uint(vmx));
                 }

@@ -51,6 +51,13 @@ int frame_block(int n_fft, int mode, const syg::FrameArgs& a, int sm_count, cuda
 }
 
 int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err) {
+#ifndef SYG_EMU
+    static size_t opted = 48 * 1024;                // float64 S_db tile: 32 x (n_mels + 1) x 8 B exceeds 48 KB for n_mels > 191
+    if (smem > opted) {
+        LCK(cudaFuncSetAttribute(sygdev::finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted = smem;
+    }
+#endif
     SYG_LAUNCH(sygdev::finalize_kernel, dim3(grid_x, grid_y), dim3(sygdev::kThreads), smem, st, a);
     LCK(cudaGetLastError());
     return 0;

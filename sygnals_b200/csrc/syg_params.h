@@ -80,7 +80,7 @@ struct FinalizeArgs {
     long long n_units;
     int T, n_rows;
     int n_mels, n_mfcc, row_mfcc;       // row_mfcc < 0: no mfcc
-    const float* dct;                   // [n_mfcc][n_mels] (lifter folded in)
+    const double* dct;                  // [n_mfcc][n_mels] float64 (lifter folded in)
     int nb, row_contrast;               // nb == 0: no contrast
     float amin, top_db;
     const float* melws;

@@ -134,7 +134,7 @@ inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
     // the group's taps are interleaved [step][lane] so one LDG.128 per step is a fully coalesced 512-byte read.
     //   desc[slot] = {filter, first padded word (multiple of 4), L, offset of the group's taps in float4 units}
     auto ppad = [](int k) { return k + ((k >> 5) << 2); };
-    const int ps_words = ((n_bins + 4 * (n_bins >> 5) + 4 + 3) / 4) * 4;      // = WarpTile::PS
+    const int ps_words = ((n_bins + 4 * (n_bins >> 5) + 16 + 3) / 4) * 4;     // = WarpTile::PS
     std::vector<int> order(t.n_mels);
     for (int i = 0; i < t.n_mels; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return t.len[a] > t.len[b]; });
@@ -150,6 +150,7 @@ inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
             pst[j] = ppad(t.start[m]) & ~3;
             L = std::max(L, (ppad(t.start[m] + t.len[m] - 1) - pst[j] + 1 + 3) / 4);
         }
+        L = (L + 3) / 4 * 4;                                      // the kernel sweeps four steps per iteration
         for (int j = 0; j < gn; ++j) pst[j] = std::max(0, std::min(pst[j], ps_words - 4 * L));   // keep the sweep inside the buffer
         const int goff4 = (int)(s.w.size() / 4);
         s.w.resize(s.w.size() + (size_t)L * 32 * 4, 0.0f);
@@ -170,11 +171,12 @@ inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
 
 // rows [n_out][n_mels] of the DCT scipy.fftpack.dct(x, type, norm) restricted to the first n_out outputs,
 // with librosa's sinusoidal lifter folded in.
+template <class Real>
 inline bool build_dct(int n_out, int N, int type, bool ortho, double lifter, int n_mfcc_for_lifter,
-                      std::vector<float>& out, std::string& err) {
+                      std::vector<Real>& out, std::string& err) {
     if (n_out < 1 || n_out > N) { err = "n_mfcc must be in [1, n_mels]"; return false; }
     if (lifter < 0) { err = "MFCC lifter must be a non-negative number"; return false; }
-    out.assign((size_t)n_out * N, 0.0f);
+    out.assign((size_t)n_out * N, (Real)0);
     for (int k = 0; k < n_out; ++k) {
         double lift = 1.0;
         if (lifter > 0) lift = 1.0 + (lifter / 2.0) * std::sin(kPi * (double)(k + 1) / lifter);
@@ -196,7 +198,7 @@ inline bool build_dct(int n_out, int N, int type, bool ortho, double lifter, int
                 err = "unsupported dct_type/norm combination";
                 return false;
             }
-            out[(size_t)k * N + n] = (float)(v * lift);
+            out[(size_t)k * N + n] = (Real)(v * lift);
         }
     }
     return true;
