@@ -319,6 +319,7 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         if ((rc = upload_table(ctx, dk, dct, &pl.fin.dct))) return rc;
         pl.fin.n_mels = p->n_mels;
         pl.fin.n_mfcc = p->n_mfcc;
+        pl.fin.dct_fold = (p->dct_type == 2) ? 1 : 0;
         ws += (size_t)T * p->n_mels * sizeof(float);
     }
     if (mask & syg::FB_CONTRAST) {
@@ -371,7 +372,7 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
         f.unit_max = a.unit_max;
         f.out = out;
         const int gx = (pl.T + sygdev::kFinTT - 1) / sygdev::kFinTT;
-        const size_t smem = (size_t)sygdev::kFinTT * (f.n_mels + 1) * sizeof(double);
+        const size_t smem = (size_t)sygdev::kFinTT * (f.n_mels + 3) * sizeof(double);   // two folded halves (or one full tile) + padding
         for (long long u0 = 0; u0 < g.n_units; u0 += 65535) {       // gridDim.y limit
             syg::FinalizeArgs fc = f;
             fc.n_units = std::min<long long>(65535, g.n_units - u0);

@@ -14,6 +14,15 @@ namespace sygdev {
 //         (librosa.feature.spectral_contrast, frequency_domain.py:200-207).
 // --------------------------------------------------------------------------------------------------------
 
+// 10 log10(x) for x >= amin > 0 through the hardware log2 (absolute error of lg2.approx ~2^-22 -> ~1e-6 dB)
+SYG_DEVICE SYG_INLINE float db10(float x) {
+#ifdef SYG_EMU
+    return 10.0f * log10f(x);
+#else
+    return 3.0102999566398120f * __log2f(x);
+#endif
+}
+
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeArgs a) {
     SYG_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x;
@@ -25,49 +34,77 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeA
 
     if (a.row_mfcc >= 0) {
         // S_db tile in float64: the DCT accumulates in FP64 (|sum| reaches 80*sqrt(n_mels) ~ 905 and the parity bar is 1e-3
-        // absolute); converting each S_db value once here (not once per DCT row) keeps the conversion pipe out of the way
-        double* const sdb = reinterpret_cast<double*>(smem_raw);            // [kFinTT][n_mels + 1]
-        const int ld = a.n_mels + 1;
+        // absolute).  DCT-II rows are (-1)^k symmetric about the centre (cos(pi k (2(N-1-n)+1) / 2N) = (-1)^k cos(pi k (2n+1) / 2N)),
+        // so the tile is stored folded: se[n] = s[n] + s[N-1-n], so[n] = s[n] - s[N-1-n] (n < N/2; centre term of an odd N
+        // separately) and every coefficient needs H = ceil(N/2) products.  Other DCT types use the unfolded tile (se = so = s).
+        const int N = a.n_mels;
+        const int H = a.dct_fold ? (N + 1) / 2 : N;
+        const int ld = H + 1;
+        double* const se = reinterpret_cast<double*>(smem_raw);            // [kFinTT][H + 1]
+        double* const so = a.dct_fold ? se + kFinTT * ld : se;
         const float ref = fmaxf(a.amin, __uint_as_float(um[0]));
-        const float ref_db = 10.0f * log10f(ref);
+        const float ref_db = db10(ref);
         // the maximum of S_db over the unit is attained at the maximum energy
-        const float max_db = 10.0f * log10f(fmaxf(a.amin, __uint_as_float(um[0]))) - ref_db;
+        const float max_db = db10(fmaxf(a.amin, __uint_as_float(um[0]))) - ref_db;
         const float floor_db = max_db - a.top_db;
-        for (int i = tid; i < nt * a.n_mels; i += kThreads) {
-            const int tt = i / a.n_mels, m = i - tt * a.n_mels;
-            const float e = a.melws[((u * a.T) + t0 + tt) * a.n_mels + m];
-            float db = 10.0f * log10f(fmaxf(a.amin, e)) - ref_db;
-            sdb[tt * ld + m] = (double)fmaxf(db, floor_db);
+        for (int i = tid; i < nt * H; i += kThreads) {
+            const int tt = i / H, n = i - tt * H;
+            const float* row = a.melws + ((u * a.T) + t0 + tt) * N;
+            const float x = fmaxf(db10(fmaxf(a.amin, row[n])) - ref_db, floor_db);
+            if (a.dct_fold) {
+                const int n2 = N - 1 - n;
+                if (n2 != n) {
+                    const float y = fmaxf(db10(fmaxf(a.amin, row[n2])) - ref_db, floor_db);
+                    se[tt * ld + n] = (double)x + (double)y;
+                    so[tt * ld + n] = (double)x - (double)y;
+                } else {
+                    se[tt * ld + n] = (double)x;
+                    so[tt * ld + n] = 0.0;
+                }
+            } else {
+                se[tt * ld + n] = (double)x;
+            }
         }
         __syncthreads();
-        for (int i = tid; i < a.n_mfcc * kFinTT; i += kThreads) {
-            const int c = i / kFinTT, tt = i - c * kFinTT;
-            if (tt < nt) {
-                const double* d = a.dct + c * a.n_mels;
-                const double* s = sdb + tt * ld;
-                // four independent chains: a single dependent DFMA chain of n_mels links is latency bound
-                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-                int m = 0;
-                for (; m + 4 <= a.n_mels; m += 4) {
-                    acc0 = fma(__ldg(&d[m]), s[m], acc0);
-                    acc1 = fma(__ldg(&d[m + 1]), s[m + 1], acc1);
-                    acc2 = fma(__ldg(&d[m + 2]), s[m + 2], acc2);
-                    acc3 = fma(__ldg(&d[m + 3]), s[m + 3], acc3);
-                }
-                for (; m < a.n_mels; ++m) acc0 = fma(__ldg(&d[m]), s[m], acc0);
-                obase[(long long)(a.row_mfcc + c) * a.T + t0 + tt] = (float)((acc0 + acc1) + (acc2 + acc3));
+        // work item = (frame, pair of coefficients of equal parity): the pair shares every load of the folded tile
+        const int n_ev = (a.n_mfcc + 1) / 2, n_od = a.n_mfcc / 2;
+        const int it_ev = (n_ev + 1) / 2, it_od = (n_od + 1) / 2;
+        for (int i = tid; i < (it_ev + it_od) * kFinTT; i += kThreads) {
+            const int item = i / kFinTT, tt = i - item * kFinTT;
+            if (tt >= nt) continue;
+            const bool odd = item >= it_ev;
+            const int c0 = odd ? 1 + 4 * (item - it_ev) : 4 * item;
+            const int c1 = c0 + 2;
+            const bool two = c1 < a.n_mfcc;
+            const double* d0 = a.dct + (long long)c0 * N;
+            const double* d1 = a.dct + (long long)(two ? c1 : c0) * N;
+            const double* s = (odd ? so : se) + tt * ld;
+            double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;                  // two chains per coefficient (DFMA latency)
+            int n = 0;
+            for (; n + 2 <= H; n += 2) {
+                const double s0 = s[n], s1 = s[n + 1];
+                p0 = fma(__ldg(&d0[n]), s0, p0);
+                q0 = fma(__ldg(&d1[n]), s0, q0);
+                p1 = fma(__ldg(&d0[n + 1]), s1, p1);
+                q1 = fma(__ldg(&d1[n + 1]), s1, q1);
             }
+            if (n < H) {
+                p0 = fma(__ldg(&d0[n]), s[n], p0);
+                q0 = fma(__ldg(&d1[n]), s[n], q0);
+            }
+            obase[(long long)(a.row_mfcc + c0) * a.T + t0 + tt] = (float)(p0 + p1);
+            if (two) obase[(long long)(a.row_mfcc + c1) * a.T + t0 + tt] = (float)(q0 + q1);
         }
     }
     if (a.nb > 0) {
-        const float pmax_db = 10.0f * log10f(fmaxf(a.amin, __uint_as_float(um[1])));
-        const float vmax_db = 10.0f * log10f(fmaxf(a.amin, __uint_as_float(um[2])));
+        const float pmax_db = db10(fmaxf(a.amin, __uint_as_float(um[1])));
+        const float vmax_db = db10(fmaxf(a.amin, __uint_as_float(um[2])));
         for (int i = tid; i < a.nb * kFinTT; i += kThreads) {
             const int bd = i / kFinTT, tt = i - bd * kFinTT;
             if (tt < nt) {
                 const float* c = a.cws + ((u * a.T) + t0 + tt) * (2 * a.nb);
-                const float pdb = fmaxf(10.0f * log10f(fmaxf(a.amin, c[bd])), pmax_db - a.top_db);
-                const float vdb = fmaxf(10.0f * log10f(fmaxf(a.amin, c[a.nb + bd])), vmax_db - a.top_db);
+                const float pdb = fmaxf(db10(fmaxf(a.amin, c[bd])), pmax_db - a.top_db);
+                const float vdb = fmaxf(db10(fmaxf(a.amin, c[a.nb + bd])), vmax_db - a.top_db);
                 obase[(long long)(a.row_contrast + bd) * a.T + t0 + tt] = pdb - vdb;
             }
         }

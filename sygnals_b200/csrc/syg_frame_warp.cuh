@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     }
                 }
                 const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fmx, 0.0f)));
-                if (lane == 0 && mx != 0u) atomicMax(&a.unit_max[unit_of(gff, a.T, small) * 4 + 0], mx);
+                const long long uff = __shfl_sync(kFull, u, ff * G);    // unit of frame ff (all lanes take part)
+                if (lane == 0 && mx != 0u) atomicMax(&a.unit_max[uff * 4 + 0], mx);
             }
         }
 
@@ -464,8 +465,9 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     if (peak == peak) pmx = fmaxf(pmx, peak);
                     if (valley == valley) vmx = fmaxf(vmx, valley);
                 }
+                const long long uff = __shfl_sync(kFull, u, ff * G);    // unit of frame ff (all lanes take part)
                 if (lane == 0) {
-                    unsigned* um = a.unit_max + unit_of(gff, a.T, small) * 4;
+                    unsigned* um = a.unit_max + uff * 4;
                     if (pmx > 0.0f) atomicMax(&um[1], __float_as_uint(pmx));
                     if (vmx > 0.0f) atomicMax(&um[2], __float_as_uint(vmx));
                 }

@@ -46,6 +46,8 @@ static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count,
                 if (variant == 1) return frame_warp_t<FftTile<10, 32>, false, 256, 2, true>(a, sm_count, st, err);
                 if (variant == 2) return frame_warp_t<FftTile<10, 32>, false, 512, 1, true>(a, sm_count, st, err);
                 if (variant == 3) return frame_warp_t<FftTile<10, 32>, false, 512, 1, false>(a, sm_count, st, err);
+                if (variant == 4) return frame_warp_t<FftTile<10, 32>, false, 320, 2, false>(a, sm_count, st, err);
+                if (variant == 5) return frame_warp_t<FftTile<10, 32>, false, 384, 2, false>(a, sm_count, st, err);
             }
             return frame_warp_t<FftTile<10, 32>, EXTRA>(a, sm_count, st, err);
         }

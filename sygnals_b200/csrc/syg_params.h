@@ -81,6 +81,7 @@ struct FinalizeArgs {
     int T, n_rows;
     int n_mels, n_mfcc, row_mfcc;       // row_mfcc < 0: no mfcc
     const double* dct;                  // [n_mfcc][n_mels] float64 (lifter folded in)
+    int dct_fold;                       // 1: DCT-II, row k is (-1)^k symmetric about the centre -> half-length sums
     int nb, row_contrast;               // nb == 0: no contrast
     float amin, top_db;
     const float* melws;
