@@ -87,9 +87,13 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
+    # one process per core, one thread per process: numpy/scipy/BLAS thread pools inside 16 forked workers oversubscribe the
+    # host and slow the reference down ~8x (measured); the baseline should be as fast as the reference can go
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[v] = "1"
     w = WORKLOADS[args.workload]
     cores = len(os.sched_getaffinity(0))
-    n_units = args.cpu_units or max(cores * 6, 48)
+    n_units = args.cpu_units or max(cores * 24, 96)
     times, cores = cpu_reference_run(args.workload, n_units, args.steps, args.warmup)
     unit_audio = w["seg_sec"] * (1.0 - w["overlap"])                    # unique audio seconds per unit
     total_t = sum(times)
@@ -294,7 +298,7 @@ def run_native(args):
         if world == 1 and not args.no_cpu:
             # bounded CPU sample of the same workload, in a fresh process (fork pool; keeps CUDA out of the children)
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
-                   "--steps", "1", "--warmup", "0"]
+                   "--steps", "1", "--warmup", "0", "--cpu-units", str(96 * len(os.sched_getaffinity(0)))]
             try:
                 r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
                 ref = json.loads(r.stdout.strip().splitlines()[-1])
