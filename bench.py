@@ -276,7 +276,18 @@ def run_native(args):
         alg_bytes = 4.0 * total + 4.0 * out.numel()                       # unique input samples + output floats, per step
         f_ms, f_n = prof["frame"]
         z_ms, z_n = prof["finalize"]
+        # dominant kernel = the frame kernel; one launch processes one workspace chunk of units (the last chunk is shorter),
+        # so per-launch bytes / per-launch time == per-step bytes / per-step kernel time
+        launches_per_step = f_n / args.steps if args.steps else 0
         achieved = alg_bytes * args.steps / (f_ms * 1e-3) / 1e9 if f_ms > 0 else None
+        traffic = None                                                    # DRAM bytes of one launch from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tr.get("workload") == args.workload:
+                traffic = {"dram_bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"],
+                           "algorithmic_bytes_of_that_launch": tr["algorithmic_bytes"], "source": tr["source"]}
+        except Exception:
+            pass
         line = {
             "metric": "audio-sec/sec (MFCC+spectral feats)", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -286,7 +297,10 @@ def run_native(args):
                        "parallelism": f"units sharded over {world} GPU(s), no data-path collective"},
             "roofline": {"bound": "hbm", "kernel": "frame_kernel (framing+window+rFFT+fused feature epilogues)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": traffic,
+                         "kernel_launches_per_step": launches_per_step,
+                         "kernel_ms_per_launch": (f_ms / f_n) if f_n else None,
+                         "algorithmic_bytes_per_launch": (alg_bytes / launches_per_step) if launches_per_step else None,
                          "kernel_ms_per_step": f_ms / args.steps, "kernel_share_of_step": f_ms / ms if ms > 0 else None,
                          "finalize_ms_per_step": z_ms / args.steps, "algorithmic_bytes_per_step": alg_bytes},
             "clocks": clk, "gpu_launches": int(f_n + z_n),
