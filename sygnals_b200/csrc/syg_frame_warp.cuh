@@ -213,25 +213,40 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
 
         if (SYNCP) __syncthreads();
         // ---------------- real split -> |X[k]|^2 (overwrites the Z region: all pairs are pulled into registers first) ----------------
+        // Lane j pairs bin k = j + i G with bin M - k.  All addresses are lane bases plus compile-time offsets: for j >= 1
+        // the bins M - iG - j of one step share a pad block, lane 0 (bin M - iG, a block start when iG is a multiple of the
+        // block size) sits one pad group further.
         {
+            const int jz = (j == 0) ? 1 : 0;
+            const float2* const zk0 = zs + j;                           // Z[k]     at zk0[zpad(iG)] (j + iG stays in iG's block: G <= E)
+            const float2* const zm0 = zs - j;                           // Z[M - k] at zm0[c1_i], lane 0: + 1 where M - iG starts a block
+            const float2* const zm1 = zm0 + jz;
             float2 zk[E / 2 + 1], zm[E / 2 + 1];
             SYG_UNROLL
             for (int i = 0; i <= E / 2; ++i) {
-                const int k = j + i * G;
-                zk[i] = zs[zpad<LE>(k)];
-                zm[i] = zs[zpad<LE>((M - k) & (M - 1))];
+                const int kk = i * G;                                    // compile time after unrolling
+                zk[i] = zk0[kk + (kk >> LE)];
+                const int c1 = (M - kk) + ((M - kk - 1) >> LE);          // zpad(M - kk - j) + j for 1 <= j < G
+                const bool blk = ((M - kk) & (E - 1)) == 0;              // M - kk starts a pad block -> lane 0 is one slot further
+                zm[i] = blk ? zm1[c1] : zm0[c1];
             }
+            if (j == 0) zm[0] = zk[0];                                   // k = 0 pairs with itself (DC / Nyquist)
             __syncwarp();
+            float* const pk0 = pf + j;                                   // P[k]     at pk0[ppad(iG)]
+            float* const pm0 = pf - j;                                   // P[M - k] at pm0[q1_i], lane 0: + 4 where M - iG starts a 32-bin block
+            float* const pm1 = pm0 + 4 * jz;
             SYG_UNROLL
             for (int i = 0; i <= E / 2; ++i) {
-                const int k = j + i * G;
+                const int kk = i * G;
+                const int k = j + kk;
                 if (i == E / 2 && j != 0) break;
                 const float2 w = __ldg(&a.tws[k]);
                 float xkr, xki, xmr, xmi;
                 real_split(zk[i].x, zk[i].y, zm[i].x, zm[i].y, w.x, w.y, xkr, xki, xmr, xmi);
-                const int k2 = M - k;
-                pf[ppad(k)] = __fmaf_rn(xkr, xkr, xki * xki);
-                if (k2 != k) pf[ppad(k2)] = __fmaf_rn(xmr, xmr, xmi * xmi);
+                pk0[kk + ((kk >> 5) << 2)] = __fmaf_rn(xkr, xkr, xki * xki);
+                const int q1 = (M - kk) + (((M - kk - 1) >> 5) << 2);
+                const bool blk = ((M - kk) & 31) == 0;
+                if (2 * k != M) (blk ? pm1 : pm0)[q1] = __fmaf_rn(xmr, xmr, xmi * xmi);
             }
         }
         __syncwarp();
