@@ -104,6 +104,46 @@ SYG_DEVICE SYG_INLINE void dft_dif(float* xr, float* xi) {
     }
 }
 
+// --------------------------------------------------------------------------------------------------------
+// packed variant: a complex point lives in one float2 (an aligned register pair), sums and differences of a butterfly
+// are single FP32x2 instructions of sm_100 (add.f32x2 / fma.rn.f32x2 via __fadd2_rn / __ffma2_rn); rotations stay scalar
+// on the two halves (a packed complex multiply would need the swapped pair).  Same DIF network as dft_dif.
+// --------------------------------------------------------------------------------------------------------
+template <int R>
+SYG_DEVICE SYG_INLINE void rot_w(float2& d, int k) {            // d *= W_R^k
+    mul_w<R>(d.x, d.y, k);
+}
+
+template <int R, int S>
+SYG_DEVICE SYG_INLINE void dft_dif_p(float2* z) {
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
+    SYG_UNROLL
+    for (int half = R / 2; half >= 1; half >>= 1) {
+        SYG_UNROLL
+        for (int base = 0; base < R; base += 2 * half) {
+            SYG_UNROLL
+            for (int k = 0; k < half; ++k) {
+                const int i0 = (base + k) * S, i1 = (base + k + half) * S;
+                const float2 a = z[i0], b = z[i1];
+                z[i0] = __fadd2_rn(a, b);
+                const int kw = (k * (R / (2 * half))) & (R - 1);
+                const int k32 = kw * (32 / R);
+                if (k32 == 8) {                                   // (a - b) * (-i) = (d.y, -d.x): two scalar subtractions
+                    z[i1] = make_float2(a.y - b.y, b.x - a.x);
+                } else if (k32 == 16) {
+                    z[i1] = __ffma2_rn(a, neg1, b);               // b - a
+                } else if (k32 == 24) {                           // * (+i) = (-d.y, d.x)
+                    z[i1] = make_float2(b.y - a.y, a.x - b.x);
+                } else {
+                    float2 d = __ffma2_rn(b, neg1, a);            // a - b
+                    if (k32 != 0) rot_w<R>(d, kw);
+                    z[i1] = d;
+                }
+            }
+        }
+    }
+}
+
 // complex multiply by a run-time twiddle (wr + i wi)
 SYG_DEVICE SYG_INLINE void cmul(float& xr, float& xi, float wr, float wi) {
     float a = xr, b = xi;

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         const long long p0 = (long long)t * a.hop - a.cpad;
 
         // ---------------- framing + window + time-domain partial statistics ----------------
-        float xr[E], xi[E];
+        float2 z[E];
         float s_sq = 0.0f, s_sq2 = 0.0f, pk = 0.0f, pk2 = 0.0f;
         double s_sum = 0.0, s_abs = 0.0, s_sqd = 0.0;
         {
@@ -134,8 +134,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                         s_abs += (double)fabsf(v.x) + (double)fabsf(v.y);
                         s_sqd += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
                     }
-                    xr[r] = v.x * w.x;
-                    xi[r] = v.y * w.y;
+                    z[r] = __fmul2_rn(v, w);
                 }
             } else {
                 // edge / unaligned frames: a compact loop stages the zero-padded samples in the (idle) Z slice first
@@ -162,8 +161,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                         s_abs += (double)fabsf(v.x) + (double)fabsf(v.y);
                         s_sqd += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
                     }
-                    xr[r] = v.x * w.x;
-                    xi[r] = v.y * w.y;
+                    z[r] = __fmul2_rn(v, w);
                 }
                 __syncwarp();
             }
@@ -171,12 +169,9 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
 
         if (SYNCP) __syncthreads();
         // ---------------- pass 1: radix E, no twiddles; butterfly j scatters to j*E + k' ----------------
-        dft_dif<E, 1>(xr, xi);
+        dft_dif_p<E, 1>(z);
         SYG_UNROLL
-        for (int kp = 0; kp < E; ++kp) {
-            const int src = bitrev(kp, LE);
-            zs[zpad<LE>(j * E + kp)] = make_float2(xr[src], xi[src]);
-        }
+        for (int kp = 0; kp < E; ++kp) zs[zpad<LE>(j * E + kp)] = z[bitrev(kp, LE)];
         __syncwarp();
         // ---------------- pass 2: Q butterflies of radix R2 per lane, twiddles W_M^{r k} ----------------
         SYG_UNROLL
@@ -184,9 +179,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             const int b = j + q * G;
             SYG_UNROLL
             for (int r = 0; r < R2; ++r) {
-                const float2 v = zs[zpad<LE>(b + r * (M / R2))];
-                xr[q * R2 + r] = v.x;
-                xi[q * R2 + r] = v.y;
+                z[q * R2 + r] = zs[zpad<LE>(b + r * (M / R2))];
             }
         }
         __syncwarp();
@@ -199,14 +192,13 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             SYG_UNROLL
             for (int r = 1; r < R2; ++r) {
                 const float2 w = __ldg(&a.tw[(r * k) << SH]);
-                cmul(xr[q * R2 + r], xi[q * R2 + r], w.x, w.y);
+                cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
             }
-            dft_dif<R2, 1>(xr + q * R2, xi + q * R2);
+            dft_dif_p<R2, 1>(z + q * R2);
             const int ob = (b - k) * R2 + k;
             SYG_UNROLL
             for (int kp = 0; kp < R2; ++kp) {
-                const int src = q * R2 + bitrev(kp, ilog2(R2));
-                zs[zpad<LE>(ob + kp * E)] = make_float2(xr[src], xi[src]);
+                zs[zpad<LE>(ob + kp * E)] = z[q * R2 + bitrev(kp, ilog2(R2))];
             }
         }
         __syncwarp();
