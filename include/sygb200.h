@@ -134,6 +134,13 @@ int syg_features_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, c
 int syg_features_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, const syg_feature_params* p,
                           float* out_host);
 
+/* PCM16 ingest (the step before the path: sygnals/core/audio/io.py:84-95 load_audio -> librosa.load hands the reference
+ * float samples = int16 / 32768).  Same as syg_features_host_f32 for 16-bit mono PCM in host memory: half the PCIe bytes, the
+ * widening runs on the device.  syg_pcm16_to_f32 is the device-side conversion alone. */
+int syg_features_host_pcm16(syg_ctx* ctx, const int16_t* y_host, const syg_units* units, const syg_feature_params* p,
+                            float* out_host);
+int syg_pcm16_to_f32(syg_ctx* ctx, const int16_t* in_dev, float* out_dev, int64_t n, void* stream);
+
 /* compute_stft(): out [n_units][1 + n_fft/2][T]; complex64 (interleaved) / float32 magnitude / float32 power */
 int syg_stft_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, int32_t n_fft, int32_t hop_length,
                  int32_t win_length, int32_t window, int32_t center, int32_t pad_mode, int32_t out_kind,

@@ -89,6 +89,8 @@ class Library:
             "syg_frame_count": (i64, [i64, i32, i32, i32]),
             "syg_features_f32": (C.c_int, [vp, vp, PU, PP, vp, vp]),
             "syg_features_host_f32": (C.c_int, [vp, vp, PU, PP, vp]),
+            "syg_features_host_pcm16": (C.c_int, [vp, vp, PU, PP, vp]),
+            "syg_pcm16_to_f32": (C.c_int, [vp, vp, vp, i64, vp]),
             "syg_stft_f32": (C.c_int, [vp, vp, PU, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
             "syg_stft_host_f32": (C.c_int, [vp, vp, PU, i32, i32, i32, i32, i32, i32, i32, vp]),
             "syg_psd_welch_f32": (C.c_int, [vp, vp, PU, f64, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
@@ -307,10 +309,19 @@ class Engine:
         T = self.frame_count(units.unit_len, p.frame_length, p.hop_length, p.center)
         if out is None:
             out = np.empty((units.n_units, rows, T), dtype=np.float32)
+        if y_ptr is None and getattr(y, "dtype", None) == np.int16:       # 16-bit PCM: widened on the device (x / 32768)
+            y = np.ascontiguousarray(y)
+            self.lib.check(self.lib.dll.syg_features_host_pcm16(self._h, y.ctypes.data, C.byref(units), C.byref(p), out.ctypes.data))
+            return out
         if y_ptr is None:
             y = _f32c(y)
             y_ptr = y.ctypes.data
         self.lib.check(self.lib.dll.syg_features_host_f32(self._h, y_ptr, C.byref(units), C.byref(p), out.ctypes.data))
+        return out
+
+    def features_host_pcm16(self, y_ptr: int, units: SygUnits, p: SygFeatureParams, out: np.ndarray) -> np.ndarray:
+        """Raw-pointer form of the PCM16 host path (pinned int16 buffer)."""
+        self.lib.check(self.lib.dll.syg_features_host_pcm16(self._h, y_ptr, C.byref(units), C.byref(p), out.ctypes.data))
         return out
 
     def stft_host(self, y: np.ndarray, units: SygUnits, n_fft: int, hop: int, win_length: int, window: int = 0,

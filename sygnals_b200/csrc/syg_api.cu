@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -62,7 +63,7 @@ struct DevBuf {
 
 struct Lane {                      // one in-flight chunk of a *_host_* call
     cudaStream_t stream = nullptr;
-    DevBuf in, out0, out1, starts, valid, ws;
+    DevBuf in, in16, out0, out1, starts, valid, ws;
 };
 
 }  // namespace
@@ -70,7 +71,7 @@ struct Lane {                      // one in-flight chunk of a *_host_* call
 struct syg_ctx {
     int device = 0;
     int sm_count = 0;
-    size_t ws_limit = (size_t)64 << 20;
+    size_t ws_limit = (size_t)1 << 30;   // 1 GiB: measured best (fewer, fuller launches); 64 MiB chunks keep the workspace in L2 but cost 5 %
     std::mutex mu;
     std::map<std::string, void*> tables;
     std::map<std::string, std::vector<int>> host_ints;
@@ -168,11 +169,18 @@ int get_window(syg_ctx* ctx, int window, int win_length, int n_fft, bool centred
 // failures as a negative SYG_E_* code plus a message.
 int launch_rc(int rc, const std::string& err) { return rc == SYG_OK ? SYG_OK : fail(rc, "%s", err.c_str()); }
 
-int launch_features(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
+// stage: 0 fused kernel, 1 / 2 the two-stage launch of the warp kernel (n_fft <= 2048 only)
+int launch_features(int n_fft, int stage, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
     std::string err;
     if (n_fft > 2048) return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_FEATURES, a, sm_count, st, err), err);
     constexpr unsigned extra = syg::FB_BANDWIDTH | syg::FB_FLATNESS | syg::FB_DOMINANT | syg::FB_MEAN_AMP | syg::FB_STD_AMP;
-    return launch_rc(syglaunch::frame_warp(n_fft, (a.mask & extra) != 0, a, sm_count, st, err), err);
+    return launch_rc(syglaunch::frame_warp(n_fft, (a.mask & extra) != 0, stage, a, sm_count, st, err), err);
+}
+
+// words per spectrum of the warp kernel (= WarpTile::PS) and frames per warp task (= WarpTile::FW)
+int warp_ps_words(int n_fft) { const int nb = n_fft / 2 + 1; return ((nb + 4 * (nb >> 5) + 16 + 3) / 4) * 4; }
+int warp_fw(int n_fft) {
+    switch (ilog2i(n_fft / 2)) { case 4: return 8; case 5: return 8; case 6: return 4; case 7: return 4; case 8: return 2; case 9: return 2; default: return 1; }
 }
 
 int launch_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
@@ -211,7 +219,9 @@ struct FeaturePlan {
     syg::FinalizeArgs fin;
     int n_rows = 0;
     int T = 0;
-    size_t ws_per_unit = 0;        // bytes of melws + cws per unit
+    size_t ws_per_unit = 0;        // bytes of melws + cws (+ spectra when two-stage) per unit
+    bool two_stage = false;        // warp kernel as FFT launch + epilogue launch (spectra through an L2-sized workspace)
+    int n_fft = 0;
 };
 
 int rows_of(const syg_feature_params* p, int32_t* n_rows) {
@@ -283,6 +293,18 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
     if (rc) return rc;
     rc = get_fft_tables(ctx, fl, &a.tw, &a.tws);
     if (rc) return rc;
+    {
+        std::string kh = keyf("twsh:%d", fl);
+        std::vector<float2> h;
+        if (!ctx->tables.count(kh)) {
+            h.resize(fl / 4 + 1);
+            for (int k = 0; k <= fl / 4; ++k) {
+                const double ang = -2.0 * sygplan::kPi * (double)k / (double)fl;
+                h[k] = make_float2((float)(0.5 * std::cos(ang)), (float)(0.5 * std::sin(ang)));
+            }
+        }
+        if ((rc = upload_table(ctx, kh, h, &a.twsh))) return rc;
+    }
     size_t ws = 0;
     if (mask & syg::FB_MFCC) {
         if (p->n_mels < 1 || p->n_mels > 256) return fail(SYG_E_UNSUPPORTED, "n_mels=%d: supported range is [1, 256]", p->n_mels);
@@ -333,6 +355,19 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         pl.fin.nb = b.nb;
         ws += (size_t)T * 2 * b.nb * sizeof(float);
     }
+    pl.n_fft = fl;
+    {
+        // two-stage launch: worth it when the epilogues dominate (they are latency bound and run at twice the occupancy on
+        // their own); SYGB200_TWO_STAGE=0/1 overrides
+        static int env = -1;
+        if (env < 0) { const char* e = std::getenv("SYGB200_TWO_STAGE"); env = e ? (std::atoi(e) ? 1 : 0) : 2; }
+        const bool heavy = (mask & syg::FB_CONTRAST) != 0 || ((mask & syg::FB_MFCC) != 0 && (mask & syg::FB_SPECSTATS) != 0);
+        (void)heavy;
+        // measured on B200 (cfg4): two stages win 4 % at 1 GiB chunks and lose 10-40 % at L2-sized chunks (launch tails), and
+        // they move 8 KB of spectrum per frame through HBM -> the fused kernel stays the default
+        pl.two_stage = fl <= 2048 && (mask & syg::FB_SPECTRUM_ANY) != 0 && env == 1;
+        if (pl.two_stage) ws += (size_t)(T + warp_fw(fl)) * warp_ps_words(fl) * sizeof(float);
+    }
     pl.ws_per_unit = ws + 4 * sizeof(unsigned);
     pl.fin.T = (int)T;
     pl.fin.n_rows = rows;
@@ -355,12 +390,22 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
     a.melws = reinterpret_cast<float*>(w + off);
     off += ((size_t)a.n_frames * pl.fin.n_mels * sizeof(float) + 255) / 256 * 256;
     a.cws = reinterpret_cast<float*>(w + off);
+    off += ((size_t)a.n_frames * 2 * pl.fin.nb * sizeof(float) + 255) / 256 * 256;
+    a.pws = reinterpret_cast<float*>(w + off);
     const bool need_fin = (a.mask & (syg::FB_MFCC | syg::FB_CONTRAST)) != 0;
     if (need_fin) CK(cudaMemsetAsync(a.unit_max, 0, (size_t)g.n_units * 4 * sizeof(unsigned), st));
     int rc;
-    {
+    if (pl.two_stage) {
+        {
+            ProfScope ps(ctx, st, PROF_FRAME);
+            rc = launch_features(n_fft, 1, a, ctx->sm_count, st);
+        }
+        if (rc) return rc;
         ProfScope ps(ctx, st, PROF_FRAME);
-        rc = launch_features(n_fft, a, ctx->sm_count, st);
+        rc = launch_features(n_fft, 2, a, ctx->sm_count, st);
+    } else {
+        ProfScope ps(ctx, st, PROF_FRAME);
+        rc = launch_features(n_fft, 0, a, ctx->sm_count, st);
     }
     if (rc) return rc;
     if (need_fin) {
@@ -392,6 +437,7 @@ size_t features_ws_bytes(const FeaturePlan& pl, long long n) {
     size_t b = ((size_t)n * 4 * sizeof(unsigned) + 255) / 256 * 256;
     b += ((size_t)n * pl.T * pl.fin.n_mels * sizeof(float) + 255) / 256 * 256;
     b += ((size_t)n * pl.T * 2 * pl.fin.nb * sizeof(float) + 255) / 256 * 256;
+    if (pl.two_stage) b += ((size_t)n * pl.T + warp_fw(pl.n_fft)) * warp_ps_words(pl.n_fft) * sizeof(float);
     return b + 256;
 }
 
@@ -438,8 +484,10 @@ int check_host_units(const syg_units* u) {
 
 // Generic chunked host pipeline: H2D of the chunk's samples, `run` on the lane's stream, D2H of up to two outputs.
 template <class Run>
-int host_pipeline(syg_ctx* ctx, const float* y_host, const syg_units* u, size_t out0_per_unit, void* out0_host,
+int host_pipeline(syg_ctx* ctx, const void* y_host_any, bool pcm16, const syg_units* u, size_t out0_per_unit, void* out0_host,
                   size_t out1_per_unit, void* out1_host, size_t ws_per_unit, long long max_chunk_units, Run run) {
+    const float* y_host = pcm16 ? nullptr : reinterpret_cast<const float*>(y_host_any);
+    const int16_t* y_host16 = pcm16 ? reinterpret_cast<const int16_t*>(y_host_any) : nullptr;
     if (u->n_units == 0) return SYG_OK;
     const size_t in_target = (size_t)128 << 20, out_target = (size_t)256 << 20;
     long long span = u->unit_starts ? u->unit_len : std::max<long long>(1, std::min(u->unit_stride, u->unit_len));
@@ -466,7 +514,15 @@ int host_pipeline(syg_ctx* ctx, const float* y_host, const syg_units* u, size_t 
         if (ws_per_unit && (rc = L.ws.ensure(ws_per_unit * n + 4096))) return rc;
         // the lane's previous chunk must have left its buffers (same stream => ordered); host-side staging
         // vectors are reused, so wait for the previous upload of this lane's tables
-        if (e > b) CK(cudaMemcpyAsync(L.in.p, y_host + b, (size_t)(e - b) * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        if (e > b && !pcm16) CK(cudaMemcpyAsync(L.in.p, y_host + b, (size_t)(e - b) * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        if (e > b && pcm16) {                                           // half the PCIe bytes; widened to float32 on the device
+            if ((rc = L.in16.ensure((size_t)(e - b) * sizeof(int16_t)))) return rc;
+            CK(cudaMemcpyAsync(L.in16.p, y_host16 + b, (size_t)(e - b) * sizeof(int16_t), cudaMemcpyHostToDevice, L.stream));
+            std::string err;
+            const int crc = syglaunch::pcm16_to_f32(reinterpret_cast<const short*>(L.in16.p), reinterpret_cast<float*>(L.in.p), e - b,
+                                                    ctx->sm_count, L.stream, err);
+            if (crc) return fail(crc, "%s", err.c_str());
+        }
         syg_units cu;
         cu.n_units = n;
         cu.unit_len = u->unit_len;
@@ -622,7 +678,7 @@ void syg_ctx_destroy(syg_ctx* ctx) {
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     ctx->ws.release();
     for (auto& l : ctx->lanes) {
-        l.in.release(); l.out0.release(); l.out1.release(); l.starts.release(); l.valid.release(); l.ws.release();
+        l.in.release(); l.in16.release(); l.out0.release(); l.out1.release(); l.starts.release(); l.valid.release(); l.ws.release();
         if (l.stream) cudaStreamDestroy(l.stream);
     }
     delete ctx;
@@ -724,8 +780,8 @@ int syg_features_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, c
     return SYG_OK;
 }
 
-int syg_features_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, const syg_feature_params* p,
-                          float* out_host) {
+static int features_host_impl(syg_ctx* ctx, const void* y_host, bool pcm16, const syg_units* units, const syg_feature_params* p,
+                              float* out_host) {
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     int rc = check_host_units(units);
     if (rc) return rc;
@@ -738,7 +794,7 @@ int syg_features_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* un
     if (!out_host) return fail(SYG_E_BADARG, "out_host is NULL");
     const size_t out_per_unit = (size_t)pl.n_rows * pl.T * sizeof(float);
     const int n_fft = p->frame_length;
-    return host_pipeline(ctx, y_host, units, out_per_unit, out_host, 0, nullptr, features_ws_bytes(pl, 1), 1LL << 40,
+    return host_pipeline(ctx, y_host, pcm16, units, out_per_unit, out_host, 0, nullptr, features_ws_bytes(pl, 1), 1LL << 40,
                          [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long n) -> int {
                              int r = L.ws.ensure(features_ws_bytes(pl, n));
                              if (r) return r;
@@ -746,6 +802,26 @@ int syg_features_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* un
                              return run_features_chunk(ctx, pl, y_dev + shift, g, reinterpret_cast<float*>(L.out0.p), L.ws.p,
                                                        n_fft, L.stream);
                          });
+}
+
+int syg_features_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, const syg_feature_params* p,
+                          float* out_host) {
+    return features_host_impl(ctx, y_host, false, units, p, out_host);
+}
+
+int syg_features_host_pcm16(syg_ctx* ctx, const int16_t* y_host, const syg_units* units, const syg_feature_params* p,
+                            float* out_host) {
+    return features_host_impl(ctx, y_host, true, units, p, out_host);
+}
+
+int syg_pcm16_to_f32(syg_ctx* ctx, const int16_t* in_dev, float* out_dev, int64_t n, void* stream) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!in_dev || !out_dev))) return fail(SYG_E_BADARG, "bad pcm16 buffer");
+    CK(cudaSetDevice(ctx->device));
+    std::string err;
+    const int rc = syglaunch::pcm16_to_f32(reinterpret_cast<const short*>(in_dev), out_dev, n, ctx->sm_count,
+                                           reinterpret_cast<cudaStream_t>(stream), err);
+    return rc ? fail(rc, "%s", err.c_str()) : SYG_OK;
 }
 
 static size_t stft_elem_bytes(int out_kind) { return out_kind == SYG_OUT_COMPLEX ? 2 * sizeof(float) : sizeof(float); }
@@ -786,7 +862,7 @@ int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units,
     if (!out_host) return fail(SYG_E_BADARG, "out_host is NULL");
     const size_t out_per_unit = (size_t)(n_fft / 2 + 1) * a.T * stft_elem_bytes(out_kind);
     const int sm = ctx->sm_count;
-    return host_pipeline(ctx, y_host, units, out_per_unit, out_host, 0, nullptr, 0, 1LL << 40,
+    return host_pipeline(ctx, y_host, false, units, out_per_unit, out_host, 0, nullptr, 0, 1LL << 40,
                          [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long n) -> int {
                              syg::FrameArgs c = a;
                              c.y = y_dev + shift;
@@ -832,7 +908,7 @@ int syg_psd_welch_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* u
     const size_t psd_per_unit = (size_t)(pl.nfft / 2 + 1) * sizeof(float);
     const size_t st_per_unit = stats_host ? 3 * sizeof(float) : 0;
     const int sm = ctx->sm_count;
-    return host_pipeline(ctx, y_host, units, psd_per_unit, psd_host, st_per_unit, stats_host, 0, 1LL << 40,
+    return host_pipeline(ctx, y_host, false, units, psd_per_unit, psd_host, st_per_unit, stats_host, 0, 1LL << 40,
                          [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long) -> int {
                              syg::WelchArgs c = pl.wa;
                              c.y = y_dev + shift;

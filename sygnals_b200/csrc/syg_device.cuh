@@ -248,6 +248,19 @@ SYG_DEVICE SYG_INLINE void real_split(float zkr, float zki, float zmr, float zmi
     xmr = ar - ci; xmi = -(ai + cr);                                  // X[M-k] = conj(A + i C)
 }
 
+// Power of the bin pair (k, M-k) straight from the packed pair (Z[k], Z[M-k]) and Wh = 0.5 exp(-2 pi i k / N):
+//   S = Zk + Zm, D = Zk - Zm (one FP32x2 instruction each);  A = (S.x, D.y)/2, B = (D.x, S.y)/2, C = W B = Wh (D.x, S.y);
+//   X[k] = A - iC = (S.x/2 + C.y, D.y/2 - C.x),  X[M-k] = conj(A + iC) = (S.x/2 - C.y, -(D.y/2 + C.x)).
+SYG_DEVICE SYG_INLINE void split_power(float2 zk, float2 zm, float2 wh, float& pk, float& pm) {
+    const float2 S = __fadd2_rn(zk, zm);
+    const float2 D = __ffma2_rn(zm, make_float2(-1.0f, -1.0f), zk);
+    const float cr = __fmaf_rn(D.x, wh.x, -S.y * wh.y), ci = __fmaf_rn(D.x, wh.y, S.y * wh.x);
+    const float ur = __fmaf_rn(S.x, 0.5f, ci), ui = __fmaf_rn(D.y, 0.5f, -cr);
+    const float vr = __fmaf_rn(S.x, 0.5f, -ci), vi = __fmaf_rn(D.y, 0.5f, cr);
+    pk = __fmaf_rn(ur, ur, ui * ui);
+    pm = __fmaf_rn(vr, vr, vi * vi);
+}
+
 // --------------------------------------------------------------------------------------------------------
 // thread-group collectives.  Groups are G consecutive threads (G a power of two, 1..kThreads); every thread of
 // the CTA calls them (lock step).  scratch: kThreads/32 doubles of shared memory.

@@ -72,14 +72,16 @@ SYG_DEVICE SYG_INLINE double lanes_scan_incl(double v, int gl) {
     return v;
 }
 
-// SYNCP: CTA barriers at the phase boundaries.  Not needed for correctness (warps own disjoint shared-memory slices);
-// they keep the warps of a CTA inside the same code region, which is what the instruction caches want: the per-frame
-// code is ~6000 straight-line instructions, several times the L1.5 instruction cache.
+// STAGE 0: fused (framing -> FFT -> |X|^2 in shared memory -> all epilogues).
+// STAGE 1 + STAGE 2: the same code as two launches.  Stage 1 (FFT, 128 registers, 16 warps/SM) stores |X|^2 to a workspace
+// that the host sizes to stay in L2; stage 2 (epilogues, 64 registers, 32 warps/SM) stages it into shared memory.  The
+// epilogues are latency bound (serial REDUX pops, min/max networks, dependent loads): twice the resident warps hide what the
+// fused kernel's 4 warps per scheduler cannot.  (CTA barriers between phases were measured and rejected: +8 %.)
 SYG_DEVICE SYG_INLINE long long unit_of(long long frame, int T, bool small) {
     return small ? (long long)((unsigned)frame / (unsigned)T) : frame / T;
 }
 
-template <class TL, bool EXTRA, int NT, int MINB, bool SYNCP>
+template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameArgs a) {
     using WT = WarpTile<TL, NT>;
     constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, ZS = WT::ZS, PS = WT::PS, LE = WT::LOG2E;
@@ -89,13 +91,15 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int f = lane / G, j = lane % G;
-    float* const wbase = reinterpret_cast<float*>(smem_raw) + warp * WT::warp_floats;
-    float* const pww = wbase;                                         // [FW][RS]  Z (float2, zpad layout), later |X|^2 (ppad layout)
-    float2* const zs = reinterpret_cast<float2*>(wbase + f * WT::RS);
-    float* const pf = wbase + f * WT::RS;
+    constexpr int RSS = (STAGE == 2) ? PS : WT::RS;                   // floats per frame region of this launch
+    constexpr int WF = FW * RSS;                                      // floats per warp
+    float* const wbase = reinterpret_cast<float*>(smem_raw) + warp * WF;
+    float* const pww = wbase;                                         // [FW][RSS]  Z (float2, zpad layout), later |X|^2 (ppad layout)
+    float2* const zs = reinterpret_cast<float2*>(wbase + f * RSS);
+    float* pf = wbase + f * RSS;
 
     // pad / slack words of the spectra are read (with zero weight) by the mel sweep: they must never hold NaN patterns
-    for (int i = lane; i < WT::warp_floats; i += 32) wbase[i] = 0.0f;
+    for (int i = lane; i < WF; i += 32) wbase[i] = 0.0f;
     __syncwarp();
 
     const long long n_tasks = (a.n_frames + FW - 1) / FW;
@@ -111,9 +115,13 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         if (!valid) ur.valid = 0;
         const long long p0 = (long long)t * a.hop - a.cpad;
 
+        float* const orow = a.out + (long long)u * a.n_rows * a.T + t;
+        if (STAGE != 2) {
+        if (STAGE == 1) pf = a.pws + gf * PS;                            // stage 1: the spectrum goes to the workspace (rows exist for every task frame)
         // ---------------- framing + window + time-domain partial statistics ----------------
         float2 z[E];
-        float s_sq = 0.0f, s_sq2 = 0.0f, pk = 0.0f, pk2 = 0.0f;
+        float2 sq2 = make_float2(0.0f, 0.0f);
+        float pk = 0.0f, pk2 = 0.0f;
         double s_sum = 0.0, s_abs = 0.0, s_sqd = 0.0;
         {
             const float* src = a.y + ur.start + p0;
@@ -125,8 +133,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     const int c = j + r * G;
                     const float2 v = __ldg(reinterpret_cast<const float2*>(src) + c);
                     const float2 w = __ldg(w2 + c);
-                    s_sq = __fmaf_rn(v.x, v.x, s_sq);
-                    s_sq2 = __fmaf_rn(v.y, v.y, s_sq2);
+                    sq2 = __ffma2_rn(v, v, sq2);
                     pk = fmaxf(pk, fabsf(v.x));
                     pk2 = fmaxf(pk2, fabsf(v.y));
                     if (EXTRA) {
@@ -152,8 +159,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     const int c = j + r * G;
                     const float2 v = reinterpret_cast<const float2*>(st)[c];
                     const float2 w = __ldg(w2 + c);
-                    s_sq = __fmaf_rn(v.x, v.x, s_sq);
-                    s_sq2 = __fmaf_rn(v.y, v.y, s_sq2);
+                    sq2 = __ffma2_rn(v, v, sq2);
                     pk = fmaxf(pk, fabsf(v.x));
                     pk2 = fmaxf(pk2, fabsf(v.y));
                     if (EXTRA) {
@@ -167,7 +173,6 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             }
         }
 
-        if (SYNCP) __syncthreads();
         // ---------------- pass 1: radix E, no twiddles; butterfly j scatters to j*E + k' ----------------
         dft_dif_p<E, 1>(z);
         SYG_UNROLL
@@ -183,7 +188,6 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             }
         }
         __syncwarp();
-        if (SYNCP) __syncthreads();
         SYG_UNROLL
         for (int q = 0; q < Q; ++q) {
             const int b = j + q * G;
@@ -203,7 +207,6 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         }
         __syncwarp();
 
-        if (SYNCP) __syncthreads();
         // ---------------- real split -> |X[k]|^2 (overwrites the Z region: all pairs are pulled into registers first) ----------------
         // Lane j pairs bin k = j + i G with bin M - k.  All addresses are lane bases plus compile-time offsets: for j >= 1
         // the bins M - iG - j of one step share a pad block, lane 0 (bin M - iG, a block start when iG is a multiple of the
@@ -232,22 +235,21 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 const int kk = i * G;
                 const int k = j + kk;
                 if (i == E / 2 && j != 0) break;
-                const float2 w = __ldg(&a.tws[k]);
-                float xkr, xki, xmr, xmi;
-                real_split(zk[i].x, zk[i].y, zm[i].x, zm[i].y, w.x, w.y, xkr, xki, xmr, xmi);
-                pk0[kk + ((kk >> 5) << 2)] = __fmaf_rn(xkr, xkr, xki * xki);
+                const float2 wh = __ldg(&a.twsh[k]);
+                float pwk, pwm;
+                split_power(zk[i], zm[i], wh, pwk, pwm);
+                pk0[kk + ((kk >> 5) << 2)] = pwk;
                 const int q1 = (M - kk) + (((M - kk - 1) >> 5) << 2);
                 const bool blk = ((M - kk) & 31) == 0;
-                if (2 * k != M) (blk ? pm1 : pm0)[q1] = __fmaf_rn(xmr, xmr, xmi * xmi);
+                if (2 * k != M) (blk ? pm1 : pm0)[q1] = pwm;
             }
         }
         __syncwarp();
 
-        float* const orow = a.out + (long long)u * a.n_rows * a.T + t;
 
         // ---------------- time-domain features (unwindowed, zero-padded frame) ----------------
         if (a.mask & syg::FB_TIME_ANY) {
-            const float tsq = lanes_sum<G>(s_sq + s_sq2);
+            const float tsq = lanes_sum<G>(sq2.x + sq2.y);
             const float tpk = lanes_max<G>(fmaxf(pk, pk2));
             if (j == 0 && valid) {
                 const float rms = sqrtf(tsq * (1.0f / (float)TL::NFFT));
@@ -272,7 +274,25 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             }
         }
 
-        if (SYNCP) __syncthreads();
+        }  // STAGE != 2
+        if (STAGE == 2) {                                                // stage 2: bring the task's spectra into shared memory
+            SYG_UNROLL
+            for (int ff = 0; ff < FW; ++ff) {
+                const float4* src = reinterpret_cast<const float4*>(a.pws + (task * FW + ff) * PS);
+                float4* dst = reinterpret_cast<float4*>(pww + ff * RSS);
+                constexpr int IM = (M + ((M >> 5) << 2)) / 4;            // float4 that holds bin M (its first word)
+                for (int i = lane; i < PS / 4; i += 32) {
+                    // the workspace's pad and slack words are never written: they read as zeros here (the mel sweep multiplies
+                    // them by zero weights, which must not meet NaN patterns)
+                    float4 v = __ldg(src + i);
+                    if (i % 9 == 8 || i > IM) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    else if (i == IM) { v.y = 0.0f; v.z = 0.0f; v.w = 0.0f; }
+                    dst[i] = v;
+                }
+            }
+            __syncwarp();
+        }
+        if (STAGE != 1) {
         // ---------------- per-frame spectral statistics (lane j owns bins [j*E, j*E+E), last lane also bin M) ----------------
         if (a.mask & syg::FB_SPECSTATS) {
             const int k0 = j * E;
@@ -401,14 +421,13 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             }
         }
 
-        if (SYNCP) __syncthreads();
         // ---------------- mel energies: one filter per lane, 32 filters of similar span per sweep (syg_plan.h) ----------------
         if (a.mask & syg::FB_MFCC) {
             const float4* const mw4 = reinterpret_cast<const float4*>(a.mel_pw);
             for (int ff = 0; ff < FW; ++ff) {
                 const long long gff = task * FW + ff;
                 if (gff >= a.n_frames) break;
-                const float* pfr = pww + ff * WT::RS;
+                const float* pfr = pww + ff * RSS;
                 float fmx = 0.0f;
                 for (int base = 0; base < a.n_mels; base += 32) {
                     const int slot = min(base + lane, a.n_mels - 1);
@@ -417,7 +436,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     const float4* pp4 = reinterpret_cast<const float4*>(pfr + d.y);
                     float acc = 0.0f;
                     if (a.mel_power_is_2) {
-                        float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                        float2 m01 = make_float2(0.0f, 0.0f), m23 = m01;
 #ifndef SYG_EMU
 #pragma unroll 1
 #endif
@@ -426,13 +445,11 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                             for (int c = 0; c < 4; ++c) {
                                 const float4 w = __ldg(wv + 32 * (i + c));
                                 const float4 q = pp4[i + c];
-                                acc = __fmaf_rn(w.x, q.x, acc);
-                                a1 = __fmaf_rn(w.y, q.y, a1);
-                                a2 = __fmaf_rn(w.z, q.z, a2);
-                                a3 = __fmaf_rn(w.w, q.w, a3);
+                                m01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(q.x, q.y), m01);
+                                m23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(q.z, q.w), m23);
                             }
                         }
-                        acc = (acc + a1) + (a2 + a3);
+                        acc = (m01.x + m01.y) + (m23.x + m23.y);
                     } else {
                         for (int i = 0; i < d.z; ++i) {
                             const float4 w = __ldg(wv + 32 * i);
@@ -454,13 +471,12 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             }
         }
 
-        if (SYNCP) __syncthreads();
         // ---------------- spectral contrast: per band mean of the n largest / n smallest magnitudes ----------------
         if (a.mask & syg::FB_CONTRAST) {
             for (int ff = 0; ff < FW; ++ff) {
                 const long long gff = task * FW + ff;
                 if (gff >= a.n_frames) break;
-                const float* pp = pww + ff * WT::RS;
+                const float* pp = pww + ff * RSS;
                 float pmx = 0.0f, vmx = 0.0f;
                 for (int bd = 0; bd < a.nb; ++bd) {
                     float peak, valley;
@@ -480,8 +496,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 }
             }
         }
+        }  // STAGE != 1
         __syncwarp();                                                   // smem slices are reused by the next task
-        if (SYNCP) __syncthreads();
     }
 }
 

@@ -8,7 +8,8 @@
 namespace syglaunch {
 // all return 0 or a negative SYG_E_* code (-3 CUDA, -5 unsupported) with a message in err
 int frame_block(int n_fft, int mode, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
-int frame_warp(int n_fft, bool extra, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
+int frame_warp(int n_fft, bool extra, int stage, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err);
+int pcm16_to_f32(const short* in, float* out, long long n, int sm_count, cudaStream_t st, std::string& err);
 int welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err);
 }  // namespace syglaunch

@@ -1,4 +1,4 @@
-// dispatch of the warp-synchronous feature kernel over n_fft (included by the two warp translation units)
+// dispatch of the warp-synchronous feature kernel over n_fft (included by the warp translation units)
 #pragma once
 
 #include <cstdlib>
@@ -8,15 +8,17 @@
 
 namespace syglaunch {
 
-template <class TL, bool EXTRA, int NT = sygdev::kThreads, int MINB = 2, bool SYNCP = false>
+// STAGE 0: fused kernel; 1: FFT -> spectra workspace; 2: spectra workspace -> features (see syg_frame_warp.cuh)
+template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using WT = sygdev::WarpTile<TL, NT>;
     static int blocks_per_sm = 0;
-    auto kfn = sygdev::frame_warp_kernel<TL, EXTRA, NT, MINB, SYNCP>;
+    auto kfn = sygdev::frame_warp_kernel<TL, EXTRA, NT, MINB, STAGE>;
+    const size_t smem = (size_t)WT::kWarps * WT::FW * (STAGE == 2 ? WT::PS : WT::RS) * sizeof(float);
     if (blocks_per_sm == 0) {
-        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT::bytes));
+        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        LCK(SYG_OCCUPANCY(nb, kfn, NT, WT::bytes));
+        LCK(SYG_OCCUPANCY(nb, kfn, NT, smem));
         if (nb < 1) { err = "frame_warp kernel does not fit on an SM"; return -3; }
         blocks_per_sm = nb;
     }
@@ -24,33 +26,23 @@ static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, 
     const long long n_rounds = (a.n_frames + per_cta - 1) / per_cta;
     if (n_rounds <= 0) return 0;
     const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm);
-    SYG_LAUNCH(kfn, grid, NT, WT::bytes, st, a);
+    SYG_LAUNCH(kfn, grid, NT, smem, st, a);
     LCK(cudaGetLastError());
     return 0;
 }
 
-template <bool EXTRA>
+template <bool EXTRA, int STAGE>
 static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using namespace sygdev;
+    constexpr int MINB = (STAGE == 2) ? 4 : 2;          // stage 2: 64 registers, 32 warps per SM
     switch (ilog2i(n_fft / 2)) {
-        case 4: return frame_warp_t<FftTile<4, 4>, EXTRA>(a, sm_count, st, err);
-        case 5: return frame_warp_t<FftTile<5, 8>, EXTRA>(a, sm_count, st, err);
-        case 6: return frame_warp_t<FftTile<6, 8>, EXTRA>(a, sm_count, st, err);
-        case 7: return frame_warp_t<FftTile<7, 16>, EXTRA>(a, sm_count, st, err);
-        case 8: return frame_warp_t<FftTile<8, 16>, EXTRA>(a, sm_count, st, err);
-        case 9: return frame_warp_t<FftTile<9, 32>, EXTRA>(a, sm_count, st, err);
-        case 10: {
-            if (!EXTRA) {       // tuning variants (SYGB200_VARIANT), see DESIGN.md
-                static int variant = -1;
-                if (variant < 0) { const char* e = std::getenv("SYGB200_VARIANT"); variant = e ? std::atoi(e) : 0; }
-                if (variant == 1) return frame_warp_t<FftTile<10, 32>, false, 256, 2, true>(a, sm_count, st, err);
-                if (variant == 2) return frame_warp_t<FftTile<10, 32>, false, 512, 1, true>(a, sm_count, st, err);
-                if (variant == 3) return frame_warp_t<FftTile<10, 32>, false, 512, 1, false>(a, sm_count, st, err);
-                if (variant == 4) return frame_warp_t<FftTile<10, 32>, false, 320, 2, false>(a, sm_count, st, err);
-                if (variant == 5) return frame_warp_t<FftTile<10, 32>, false, 384, 2, false>(a, sm_count, st, err);
-            }
-            return frame_warp_t<FftTile<10, 32>, EXTRA>(a, sm_count, st, err);
-        }
+        case 4: return frame_warp_t<FftTile<4, 4>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+        case 5: return frame_warp_t<FftTile<5, 8>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+        case 6: return frame_warp_t<FftTile<6, 8>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+        case 7: return frame_warp_t<FftTile<7, 16>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+        case 8: return frame_warp_t<FftTile<8, 16>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+        case 9: return frame_warp_t<FftTile<9, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+        case 10: return frame_warp_t<FftTile<10, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
     }
     err = "n_fft=" + std::to_string(n_fft) + " has no warp tile";
     return -5;

@@ -46,6 +46,7 @@ struct FrameArgs {
     const float* window;        // [n_fft], already zero-padded/centred to n_fft
     const float2* tw;           // [M]      exp(-2 pi i k / M)
     const float2* tws;          // [M/2+1]  exp(-2 pi i k / n_fft)
+    const float2* twsh;         // [M/2+1]  0.5 exp(-2 pi i k / n_fft)   (warp feature kernel: split with the halving folded in)
     // ---- features
     unsigned mask;
     double bin_hz;              // frequency of bin 1 (numpy rfftfreq step)
@@ -71,6 +72,7 @@ struct FrameArgs {
     float* melws;               // [n_frames][n_mels]   raw mel energies
     float* cws;                 // [n_frames][2*nb]     contrast peaks | valleys (linear)
     unsigned* unit_max;         // [n_units][4]         bit images of max mel energy, max peak, max valley
+    float* pws;                 // two-stage launch only: [n_frames][PS] power spectra (ppad layout) handed from stage 1 to stage 2
     // ---- stft
     int out_kind;               // 0 complex64, 1 magnitude, 2 power
     void* stft_out;             // [n_units][B][T]

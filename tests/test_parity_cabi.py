@@ -304,3 +304,21 @@ def test_welch_vs_oracle_shapes(eng):
             f, ref = orc.compute_psd_welch(y[c * sr:(c + 1) * sr].astype(np.float64), fs=sr, nperseg=nperseg, noverlap=nov, nfft=nfft)
             assert psd[c].shape == ref.shape
             assert (np.abs(psd[c] - ref) <= 1e-4 * ref + 2e-6 * ref.max()).all()
+
+
+def test_pcm16_ingest_equals_float_path(eng):
+    """syg_features_host_pcm16: 16-bit PCM widened on the device (x / 32768, libsndfile's normalisation behind librosa.load,
+    sygnals/core/audio/io.py:84-95) must give bit-identical rows to the float32 path on the same samples."""
+    sr, n = 22050, 30000
+    rng = np.random.default_rng(9)
+    t = np.arange(n) / sr
+    pcm = np.clip(9000 * np.sin(2 * np.pi * 440 * t) + 3000 * rng.standard_normal(n), -32768, 32767).astype(np.int16)
+    pcm[:7] = [-32768, 32767, 0, 1, -1, 12345, -12345]
+    feats = ["mfcc", "spectral_centroid", "rms_energy", "crest_factor", "spectral_contrast"]
+    p = _ffi.make_params(eng.lib, sr, feats, 1024, 256, feature_params={"mfcc": {"n_mels": 40}})
+    u = eng.units_clips(3, 10000)
+    a = eng.features_host(pcm, u, p)                                  # int16 -> PCM16 entry point
+    b = eng.features_host(pcm.astype(np.float32) / np.float32(32768.0), u, p)
+    assert a.dtype == np.float32 and np.array_equal(a, b)
+    names, ref = oracle_rows(pcm[:10000].astype(np.float64) / 32768.0, sr, feats, 1024, 256, {"mfcc": {"n_mels": 40}})
+    check_rows(names, a[0], ref, bin_hz=sr / 1024)
