@@ -158,6 +158,15 @@ int syg_psd_welch_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* u
                            int32_t nperseg, int32_t noverlap, int32_t nfft, int32_t detrend_constant,
                            int32_t scaling, float* psd_host, float* stats_host);
 
+/* format_feature_vectors_per_segment() (sygnals/core/ml_utils/formatters.py:51-163): NaN-aware aggregation of each segment's
+ * frames, per row agg[r] in SYG_AGG_* (formatters.py:39-45).  Element (s, r, i) = feats_dev[off_s + r * row_stride + i],
+ * i < len_s, with off_s = seg_off_dev ? seg_off_dev[s] : s * n_rows * row_stride and len_s = seg_len_dev ? seg_len_dev[s] :
+ * fixed_len (len_s <= 0: NaN row, the reference's skipped segment).  out_dev: float64 [n_seg][n_rows].  agg is a HOST array. */
+enum { SYG_AGG_MEAN = 0, SYG_AGG_STD = 1, SYG_AGG_MEDIAN = 2, SYG_AGG_MIN = 3, SYG_AGG_MAX = 4 };
+int syg_aggregate_f32(syg_ctx* ctx, const float* feats_dev, int64_t n_seg, int32_t n_rows, int64_t row_stride,
+                      const int64_t* seg_off_dev, const int32_t* seg_len_dev, int32_t fixed_len, const int32_t* agg,
+                      double* out_dev, void* stream);
+
 /* segment_fixed_length() boundary arithmetic (segmentation.py:62-114).  seg_len/seg_hop receive the integer
  * lengths; returns the number of segments (>= 0) or a negative error. */
 int64_t syg_segment_count(int64_t total_samples, double sr, double segment_length_sec, double overlap_ratio,

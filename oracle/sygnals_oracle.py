@@ -455,3 +455,39 @@ def aggregate_frames(frames_matrix: np.ndarray, method: str) -> np.ndarray:
     """formatters.py:28-47: NaN-aware aggregate over axis 0 of a (T, n_features) block."""
     fn = {"mean": np.nanmean, "std": np.nanstd, "median": np.nanmedian, "min": np.nanmin, "max": np.nanmax}[method]
     return fn(frames_matrix, axis=0)
+
+
+# ----------------------------------------------------------------------------
+# ml_utils/formatters.py:28-47, 51-163
+# ----------------------------------------------------------------------------
+def _nanagg(func):
+    """formatters.py:28-37"""
+    def wrapper(a):
+        if a.size == 0 or np.all(np.isnan(a)):
+            return np.nan
+        valid = a[~np.isnan(a)]
+        if valid.size == 0:
+            return np.nan
+        return func(valid)
+    return wrapper
+
+
+AGGREGATION_FUNCS = {"mean": _nanagg(np.mean), "std": _nanagg(np.std), "median": _nanagg(np.median),
+                     "min": _nanagg(np.min), "max": _nanagg(np.max)}          # formatters.py:39-45
+
+
+def format_feature_vectors_per_segment(features_dict, segment_indices, aggregation="mean"):
+    """formatters.py:51-163, ``output_format='numpy'``: [n_segments, n_features] float64, NaN rows for invalid segments."""
+    names = list(features_dict.keys())
+    num_frames = len(features_dict[names[0]])
+    if isinstance(aggregation, str):
+        funcs = {n: AGGREGATION_FUNCS[aggregation] for n in names}
+    else:
+        funcs = {n: AGGREGATION_FUNCS[aggregation.get(n, "mean")] for n in names}
+    out = np.full((len(segment_indices), len(names)), np.nan, dtype=np.float64)
+    for i, (s, e) in enumerate(segment_indices):
+        if not (0 <= s < num_frames and s < e and e <= num_frames):           # formatters.py:138-147
+            continue
+        for j, n in enumerate(names):
+            out[i, j] = funcs[n](np.asarray(features_dict[n], dtype=np.float64)[s:e])
+    return out

@@ -36,6 +36,7 @@ WINDOW_IDS = {"hann": 0, "hanning": 0, "hamming": 1, "blackman": 2, "boxcar": 3,
 PAD_IDS = {"constant": 0, "reflect": 1}
 OUT_COMPLEX, OUT_MAGNITUDE, OUT_POWER = 0, 1, 2
 SCALING_IDS = {"density": 0, "spectrum": 1}
+AGG_IDS = {"mean": 0, "std": 1, "median": 2, "min": 3, "max": 4}      # formatters.py:39-45
 MAX_FEATURES = 16
 
 
@@ -95,6 +96,7 @@ class Library:
             "syg_stft_host_f32": (C.c_int, [vp, vp, PU, i32, i32, i32, i32, i32, i32, i32, vp]),
             "syg_psd_welch_f32": (C.c_int, [vp, vp, PU, f64, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
             "syg_psd_welch_host_f32": (C.c_int, [vp, vp, PU, f64, i32, i32, i32, i32, i32, i32, vp, vp]),
+            "syg_aggregate_f32": (C.c_int, [vp, vp, i64, i32, i64, vp, vp, i32, vp, vp, vp]),
             "syg_segment_count": (i64, [i64, f64, f64, f64, i32, f64, C.POINTER(i64), C.POINTER(i64)]),
             "syg_segment_table": (i64, [i64, f64, f64, f64, i32, f64, vp, vp, i64]),
             "syg_debug_window": (C.c_int, [i32, i32, i32, vp]),
@@ -362,6 +364,13 @@ class Engine:
         self.lib.check(self.lib.dll.syg_psd_welch_f32(self._h, y_ptr, C.byref(units), float(fs), int(window), int(nperseg),
                                                       int(noverlap), int(nfft), int(bool(detrend)), int(scaling), psd_ptr,
                                                       stats_ptr or None, stream or None))
+
+    def aggregate_dev(self, feats_ptr: int, n_seg: int, n_rows: int, row_stride: int, agg_ids: Sequence[int], out_ptr: int,
+                      seg_off_ptr: int = 0, seg_len_ptr: int = 0, fixed_len: int = 0, stream: int = 0) -> None:
+        """format_feature_vectors_per_segment on device buffers (float32 in, float64 [n_seg, n_rows] out)."""
+        agg = (C.c_int32 * max(1, n_rows))(*[int(a) for a in agg_ids])
+        self.lib.check(self.lib.dll.syg_aggregate_f32(self._h, feats_ptr, int(n_seg), int(n_rows), int(row_stride), seg_off_ptr or None,
+                                                      seg_len_ptr or None, int(fixed_len), C.addressof(agg), out_ptr, stream or None))
 
     # ------------------------------------------------------------------ pinned host memory
     def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:

@@ -919,6 +919,22 @@ int syg_psd_welch_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* u
                          });
 }
 
+int syg_aggregate_f32(syg_ctx* ctx, const float* feats_dev, int64_t n_seg, int32_t n_rows, int64_t row_stride,
+                      const int64_t* seg_off_dev, const int32_t* seg_len_dev, int32_t fixed_len, const int32_t* agg,
+                      double* out_dev, void* stream) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    if (n_seg < 0 || n_rows < 0 || row_stride < 0) return fail(SYG_E_BADARG, "negative aggregation geometry");
+    if (n_seg == 0 || n_rows == 0) return SYG_OK;
+    if (!feats_dev || !out_dev || !agg) return fail(SYG_E_BADARG, "NULL pointer");
+    for (int i = 0; i < n_rows && i < 64; ++i)
+        if (agg[i] < SYG_AGG_MEAN || agg[i] > SYG_AGG_MAX) return fail(SYG_E_BADARG, "unknown aggregation id %d", agg[i]);
+    CK(cudaSetDevice(ctx->device));
+    std::string err;
+    const int rc = syglaunch::aggregate(feats_dev, n_seg, n_rows, row_stride, reinterpret_cast<const long long*>(seg_off_dev), seg_len_dev,
+                                        fixed_len, agg, out_dev, ctx->sm_count, reinterpret_cast<cudaStream_t>(stream), err);
+    return rc ? fail(rc, "%s", err.c_str()) : SYG_OK;
+}
+
 int64_t syg_segment_count(int64_t total_samples, double sr, double segment_length_sec, double overlap_ratio,
                           int32_t pad, double min_segment_length_sec, int64_t* seg_len, int64_t* seg_hop) {
     std::string err;

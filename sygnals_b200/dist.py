@@ -135,10 +135,12 @@ def segment_features_sharded(y, sr: int, segment_length_sec: float, features: Se
                              pad: bool = True, min_segment_length_sec: Optional[float] = None, frame_length: int = 2048,
                              hop_length: int = 512, center: bool = True, window: str = "hann",
                              feature_params: Optional[dict] = None, rank: Optional[int] = None, world: Optional[int] = None,
-                             gather: bool = True, group=None, engine: Optional[_ffi.Engine] = None) -> Dict[str, object]:
+                             gather: bool = True, group=None, engine: Optional[_ffi.Engine] = None,
+                             aggregation=None) -> Dict[str, object]:
     """``batch.segment_features`` over ``world`` ranks: each rank slices its sample range (block + halo) out of ``y`` (every
     rank is handed the same recording, or at least its own range of it), runs the fused kernels on its block of segments and
-    -- if ``gather`` -- takes part in the final all-gather.  Returns {'names', 'features', 'plan'}."""
+    -- if ``gather`` -- takes part in the final all-gather.  ``aggregation`` ('mean' | 'std' | 'median' | 'min' | 'max' or a
+    per-feature dict) reduces every segment's frames on the device first.  Returns {'names', 'features', 'plan'}."""
     if rank is None or world is None:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -149,5 +151,13 @@ def segment_features_sharded(y, sr: int, segment_length_sec: float, features: Se
     plan = plan_segments(int(y.shape[0]), sr, segment_length_sec, overlap_ratio, pad, min_segment_length_sec, rank, world, lib)
     local = run_shard(y[plan.sample_begin:plan.sample_end], plan, sr, features, frame_length, hop_length, center, window,
                       feature_params, engine)
+    names = feature_row_names(features, feature_params)
+    if aggregation is not None:
+        # format_feature_vectors_per_segment (formatters.py:51-163) on the device BEFORE the gather: the collective carries
+        # [segments, rows] instead of [segments, rows, T]
+        if not (_is_torch(local) and local.is_cuda):
+            raise ValueError("aggregation= needs the device path (a CUDA tensor as input)")
+        from .core.ml_utils.formatters import aggregate_segments
+        local = aggregate_segments(local, names, aggregation)
     out = gather_features(local, plan, group) if gather else local
-    return {"names": feature_row_names(features, feature_params), "features": out, "plan": plan}
+    return {"names": names, "features": out, "plan": plan}

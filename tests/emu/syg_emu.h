@@ -266,6 +266,7 @@ static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -116,3 +116,39 @@ def test_cfg5_machinery_64_channels():
         rms = np.sqrt(np.mean(x * x))
         np.testing.assert_allclose(st[u, 0].item(), rms, rtol=1e-5)
         np.testing.assert_allclose(st[u, 1].item(), np.abs(x).max() / rms, rtol=1e-5)
+
+
+def test_segment_aggregation_on_device_and_mirror():
+    torch = _torch()
+    from oracle import sygnals_oracle as orc
+    from sygnals_b200 import batch, dist as sdist
+    from sygnals_b200.core.ml_utils import formatters as F
+    from sygnals_b200.utils import synth
+    sr = 44100
+    y = torch.empty(600 * sr, dtype=torch.float32, device="cuda")
+    synth.torch_mixture_(y, sr, seed=3, unit=sr)
+    r = batch.segment_features(y, sr, 2.0, CFG4_FEATURES, overlap_ratio=0.5)
+    feats, names = r["features"], r["names"]
+    agg = {"mfcc_0": "median", "spectral_centroid": "std", "rms_energy": "max", "crest_factor": "min"}
+    dev = F.aggregate_segments(feats, names, agg)
+    torch.cuda.synchronize()
+    assert tuple(dev.shape) == (feats.shape[0], 24) and dev.dtype == torch.float64
+    h = feats.cpu().numpy().astype(np.float64)
+    for s in (0, 17, feats.shape[0] - 1):
+        ref = orc.format_feature_vectors_per_segment({n: h[s, j] for j, n in enumerate(names)}, [(0, h.shape[2])], agg)[0]
+        np.testing.assert_allclose(dev[s].cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
+    # sharded entry point with on-device aggregation (single rank here: no process group) == aggregate of the plain result
+    sh = sdist.segment_features_sharded(y, sr, 2.0, CFG4_FEATURES, overlap_ratio=0.5, aggregation=agg, rank=0, world=1)
+    assert torch.equal(sh["features"], dev)
+    # drop-in mirror of the reference function on a dict of 1-D arrays with (start, end) frame tables
+    d = {n: h[5, j] for j, n in enumerate(names[:6])}
+    segs = [(0, 50), (50, 173), (10, 11), (170, 180), (0, 173)]
+    import warnings
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        got = F.format_feature_vectors_per_segment(d, segs, aggregation="median", output_format="numpy")
+        df = F.format_feature_vectors_per_segment(d, segs, aggregation="mean")
+    assert any("Invalid segment indices" in str(x.message) for x in w)
+    ref = orc.format_feature_vectors_per_segment(d, segs, "median")
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    assert list(df.columns) == names[:6] and df.index.name == "segment_index" and np.isnan(df.iloc[3]).all()

@@ -91,3 +91,21 @@ def test_shim_power_to_db_semantics():
     d = librosa_shim.power_to_db(S, ref=np.max)
     assert d.max() == 0.0 and d.min() == -80.0
     assert librosa_shim.power_to_db(np.zeros((2, 2)), ref=np.max).tolist() == [[0.0, 0.0], [0.0, 0.0]]
+
+
+@needs_ref
+def test_segment_aggregation_equals_reference():
+    import warnings as w
+    ref_loader.load_reference()
+    from sygnals.core.ml_utils.formatters import format_feature_vectors_per_segment as ref_fn
+    rng = np.random.default_rng(5)
+    feats = {f"f{i}": rng.standard_normal(300) for i in range(4)}
+    feats["f1"][rng.integers(0, 300, 40)] = np.nan
+    feats["f2"][50:90] = np.nan
+    segs = [(0, 10), (10, 11), (50, 90), (0, 300), (290, 300), (20, 20), (280, 310)]
+    for agg in ("mean", "std", "median", "min", "max", {"f0": "median", "f3": "max"}):
+        with w.catch_warnings():
+            w.simplefilter("ignore")
+            a = ref_fn(feats, segs, aggregation=agg, output_format="numpy")
+        b = O.format_feature_vectors_per_segment(feats, segs, agg)
+        np.testing.assert_array_equal(a, b)

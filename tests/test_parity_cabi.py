@@ -322,3 +322,67 @@ def test_pcm16_ingest_equals_float_path(eng):
     assert a.dtype == np.float32 and np.array_equal(a, b)
     names, ref = oracle_rows(pcm[:10000].astype(np.float64) / 32768.0, sr, feats, 1024, 256, {"mfcc": {"n_mels": 40}})
     check_rows(names, a[0], ref, bin_hz=sr / 1024)
+
+
+def _dev_buffers(eng, *arrays):
+    """'Device' copies of numpy arrays for the engine under test: CUDA tensors on the B200, the arrays themselves on the
+    CPU emulator build (whose device memory is host memory).  Returns (holders, pointers)."""
+    from backends import get_engine
+    if eng is get_engine("emu"):
+        hold = [np.ascontiguousarray(a) for a in arrays]
+        return hold, [h.ctypes.data for h in hold]
+    import torch
+    hold = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrays]
+    return hold, [h.data_ptr() for h in hold]
+
+
+def _host(eng, h):
+    return h if isinstance(h, np.ndarray) else h.cpu().numpy()
+
+
+@pytest.mark.parametrize("agg", ["mean", "std", "median", "min", "max", "mixed"])
+def test_segment_aggregation_vs_oracle(eng, agg):
+    """syg_aggregate_f32 == format_feature_vectors_per_segment (formatters.py:51-163): NaN-aware, per-feature methods,
+    invalid segments -> NaN rows, odd/even medians, negative values, single-frame segments."""
+    rng = np.random.default_rng(12)
+    names = [f"f{i}" for i in range(5)]
+    N = 400
+    feats = {n: (rng.standard_normal(N) * 10.0 ** rng.integers(-2, 3)).astype(np.float32).astype(np.float64) for n in names}
+    feats["f1"][rng.integers(0, N, 60)] = np.nan
+    feats["f2"][100:140] = np.nan                                    # one segment entirely NaN for this feature
+    feats["f3"][:] = np.round(feats["f3"])                           # many ties
+    segs = [(0, 1), (1, 3), (3, 36), (36, 100), (100, 140), (140, 141), (150, 400), (0, 400), (390, 400), (50, 50), (380, 420)]
+    aggregation = {"f0": "median", "f1": "std", "f2": "max", "f3": "median", "f4": "min"} if agg == "mixed" else agg
+    ref = orc.format_feature_vectors_per_segment(feats, segs, aggregation)
+    ids = [_ffi.AGG_IDS[aggregation.get(n, "mean") if isinstance(aggregation, dict) else aggregation] for n in names]
+    off = np.array([s if (0 <= s < N and s < e <= N) else 0 for s, e in segs], dtype=np.int64)
+    ln = np.array([e - s if (0 <= s < N and s < e <= N) else 0 for s, e in segs], dtype=np.int32)
+    mat = np.stack([feats[n].astype(np.float32) for n in names])
+    out = np.zeros((len(segs), len(names)), dtype=np.float64)
+    hold, (pm, po, pl_, pout) = _dev_buffers(eng, mat, off, ln, out)
+    eng.aggregate_dev(pm, len(segs), len(names), N, ids, pout, seg_off_ptr=po, seg_len_ptr=pl_)
+    if not isinstance(hold[3], np.ndarray):
+        import torch
+        torch.cuda.synchronize()
+    got = _host(eng, hold[3])
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    if agg in ("median", "min", "max"):
+        assert np.array_equal(got[ok], ref[ok])                      # selections of float32 values: exact
+    else:
+        np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-12, atol=1e-12)
+    # regular layout [n_seg, rows, T] without tables
+    T, n_seg = 37, 9
+    cube = rng.standard_normal((n_seg, len(names), T)).astype(np.float32)
+    cube[2, 1, 5:9] = np.nan
+    out2 = np.zeros((n_seg, len(names)), dtype=np.float64)
+    hold2, (pc, pout2) = _dev_buffers(eng, cube, out2)
+    eng.aggregate_dev(pc, n_seg, len(names), T, ids, pout2, fixed_len=T)
+    if not isinstance(hold2[1], np.ndarray):
+        import torch
+        torch.cuda.synchronize()
+    got2 = _host(eng, hold2[1])
+    for s in range(n_seg):
+        d = {n: cube[s, j].astype(np.float64) for j, n in enumerate(names)}
+        r = orc.format_feature_vectors_per_segment(d, [(0, T)], aggregation)[0]
+        np.testing.assert_allclose(got2[s], r, rtol=1e-12, atol=1e-12)
