@@ -185,6 +185,9 @@ int warp_fw(int n_fft) {
 
 int launch_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
     std::string err;
+    static int env = -1;                                                // SYGB200_STFT_BLOCK=1: the CTA-cooperative kernel for every n_fft
+    if (env < 0) { const char* e = std::getenv("SYGB200_STFT_BLOCK"); env = e ? std::atoi(e) : 0; }
+    if (n_fft <= 2048 && !env) return launch_rc(syglaunch::frame_warp_stft(n_fft, a, sm_count, st, err), err);
     return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_STFT, a, sm_count, st, err), err);
 }
 

@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     constexpr int RSS = (STAGE == 2) ? PS : WT::RS;                   // floats per frame region of this launch
     constexpr int WF = FW * RSS;                                      // floats per warp
     float* const wbase = reinterpret_cast<float*>(smem_raw) + warp * WF;
+    // STAGE 3 (STFT output): CTA tile [B][TT + 1] behind the warps' regions, TT = frames of one CTA round; + per-slot output offsets
+    constexpr int TT = WT::kWarps * FW, TTP = TT + 1;
+    long long* const slot_off = reinterpret_cast<long long*>(reinterpret_cast<float*>(smem_raw) + WT::kWarps * WF);   // [TT]
+    float* const tile = reinterpret_cast<float*>(slot_off + TT);                                                    // [B][TTP] float or float2
     float* const pww = wbase;                                         // [FW][RSS]  Z (float2, zpad layout), later |X|^2 (ppad layout)
     float2* const zs = reinterpret_cast<float2*>(wbase + f * RSS);
     float* pf = wbase + f * RSS;
@@ -144,20 +148,19 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     z[r] = __fmul2_rn(v, w);
                 }
             } else {
-                // edge / unaligned frames: a compact loop stages the zero-padded samples in the (idle) Z slice first
-                float* st = reinterpret_cast<float*>(zs);
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-                for (int i = j; i < 2 * M; i += G) {
-                    const long long pos = p0 + i;
-                    st[i] = (pos >= 0 && pos < ur.valid) ? __ldg(a.y + ur.start + pos) : 0.0f;
-                }
-                __syncwarp();
+                // edge / unaligned frames: per-sample predicated loads (zero padding by predicate; reflect padding for STFT)
+                const float* yb = a.y + ur.start;
+                const long long nv = ur.valid;
+                const bool refl = (STAGE == 3) && a.pad_mode == 1 && nv > 0;
                 SYG_UNROLL
                 for (int r = 0; r < E; ++r) {
                     const int c = j + r * G;
-                    const float2 v = reinterpret_cast<const float2*>(st)[c];
+                    const long long pos = p0 + 2 * c;
+                    float2 v = make_float2(0.0f, 0.0f);
+                    if (pos >= 0 && pos < nv) v.x = __ldg(yb + pos);
+                    else if (refl) v.x = __ldg(yb + reflect_index(pos, nv));
+                    if (pos + 1 >= 0 && pos + 1 < nv) v.y = __ldg(yb + pos + 1);
+                    else if (refl) v.y = __ldg(yb + reflect_index(pos + 1, nv));
                     const float2 w = __ldg(w2 + c);
                     sq2 = __ffma2_rn(v, v, sq2);
                     pk = fmaxf(pk, fabsf(v.x));
@@ -169,7 +172,6 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     }
                     z[r] = __fmul2_rn(v, w);
                 }
-                __syncwarp();
             }
         }
 
@@ -235,6 +237,24 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 const int kk = i * G;
                 const int k = j + kk;
                 if (i == E / 2 && j != 0) break;
+                if (STAGE == 3) {
+                    const float2 w = __ldg(&a.tws[k]);
+                    float xkr, xki, xmr, xmi;
+                    real_split(zk[i].x, zk[i].y, zm[i].x, zm[i].y, w.x, w.y, xkr, xki, xmr, xmi);
+                    const int slot = warp * FW + f;
+                    const int k2 = M - k;
+                    if (a.out_kind == 0) {
+                        float2* t2 = reinterpret_cast<float2*>(tile);
+                        t2[k * TTP + slot] = make_float2(xkr, xki);
+                        if (k2 != k) t2[k2 * TTP + slot] = make_float2(xmr, xmi);
+                    } else {
+                        float pk_ = __fmaf_rn(xkr, xkr, xki * xki), pm_ = __fmaf_rn(xmr, xmr, xmi * xmi);
+                        if (a.out_kind == 1) { pk_ = sqrtf(pk_); pm_ = sqrtf(pm_); }
+                        tile[k * TTP + slot] = pk_;
+                        if (k2 != k) tile[k2 * TTP + slot] = pm_;
+                    }
+                    continue;
+                }
                 const float2 wh = __ldg(&a.twsh[k]);
                 float pwk, pwm;
                 split_power(zk[i], zm[i], wh, pwk, pwm);
@@ -247,6 +267,31 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         __syncwarp();
 
 
+        if (STAGE == 3) {
+            // ---------------- STFT output: rows of TT consecutive frames per bin leave the CTA as contiguous runs ----------------
+            if (j == 0) slot_off[warp * FW + f] = valid ? ((long long)u * B) * a.T + t : -1;
+            __syncthreads();
+            // thread -> (slot = tid % TT, bins tid / TT + i * NT / TT): the slot, its output offset and the strides are loop constants
+            static_assert(NT % TT == 0, "the CTA covers whole tile rows per step");
+            constexpr int KS = NT / TT;
+            const int sl = tid % TT, kq = tid / TT;
+            const long long off = slot_off[sl];
+            if (off >= 0) {
+                if (a.out_kind == 0) {
+                    const float2* src = reinterpret_cast<const float2*>(tile) + kq * TTP + sl;
+                    float2* dst = reinterpret_cast<float2*>(a.stft_out) + off + (long long)kq * a.T;
+                    const long long dstep = (long long)KS * a.T;
+                    for (int k = kq; k < B; k += KS, src += KS * TTP, dst += dstep) *dst = *src;
+                } else {
+                    const float* src = tile + kq * TTP + sl;
+                    float* dst = reinterpret_cast<float*>(a.stft_out) + off + (long long)kq * a.T;
+                    const long long dstep = (long long)KS * a.T;
+                    for (int k = kq; k < B; k += KS, src += KS * TTP, dst += dstep) *dst = *src;
+                }
+            }
+            __syncthreads();                                        // the tile is refilled by the next round
+            continue;
+        }
         // ---------------- time-domain features (unwindowed, zero-padded frame) ----------------
         if (a.mask & syg::FB_TIME_ANY) {
             const float tsq = lanes_sum<G>(sq2.x + sq2.y);

@@ -12,20 +12,25 @@ namespace syglaunch {
 template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using WT = sygdev::WarpTile<TL, NT>;
-    static int blocks_per_sm = 0;
+    static int blocks_per_sm[2] = {0, 0};
     auto kfn = sygdev::frame_warp_kernel<TL, EXTRA, NT, MINB, STAGE>;
-    const size_t smem = (size_t)WT::kWarps * WT::FW * (STAGE == 2 ? WT::PS : WT::RS) * sizeof(float);
-    if (blocks_per_sm == 0) {
-        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = (size_t)WT::kWarps * WT::FW * (STAGE == 2 ? WT::PS : WT::RS) * sizeof(float);
+    const int wide = (STAGE == 3 && a.out_kind == 0) ? 1 : 0;        // complex64 tile
+    if (STAGE == 3) {
+        const int TT = WT::kWarps * WT::FW;
+        smem += (size_t)TT * sizeof(long long) + (size_t)(WT::M + 1) * (TT + 1) * (wide ? 8 : 4);
+    }
+    if (blocks_per_sm[wide] == 0) {
+        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + (STAGE == 3 && !wide ? (WT::M + 1) * (WT::kWarps * WT::FW + 1) * 4 : 0)));
         int nb = 0;
         LCK(SYG_OCCUPANCY(nb, kfn, NT, smem));
         if (nb < 1) { err = "frame_warp kernel does not fit on an SM"; return -3; }
-        blocks_per_sm = nb;
+        blocks_per_sm[wide] = nb;
     }
     const long long per_cta = (long long)WT::FW * WT::kWarps;
     const long long n_rounds = (a.n_frames + per_cta - 1) / per_cta;
     if (n_rounds <= 0) return 0;
-    const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm);
+    const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm[wide]);
     SYG_LAUNCH(kfn, grid, NT, smem, st, a);
     LCK(cudaGetLastError());
     return 0;
