@@ -58,7 +58,11 @@ enum {
     SYG_FEAT_DOMINANT_FREQUENCY = 9,
     SYG_FEAT_MEAN_AMPLITUDE = 10,
     SYG_FEAT_STD_DEV_AMPLITUDE = 11,
-    SYG_FEAT_COUNT_ = 12
+    SYG_FEAT_ZERO_CROSSING_RATE = 12, /* audio/features.py:26-71 (librosa: edge padding, threshold 1e-10) */
+    SYG_FEAT_SKEWNESS = 13,           /* time_domain.py:67-97   scipy.stats.skew(bias=False)               */
+    SYG_FEAT_KURTOSIS = 14,           /* time_domain.py:99-126  scipy.stats.kurtosis(fisher, bias=False)   */
+    SYG_FEAT_SIGNAL_ENTROPY = 15,     /* time_domain.py:186-227 numpy.histogram(num_bins) + entropy        */
+    SYG_FEAT_COUNT_ = 16
 };
 
 enum { SYG_WINDOW_HANN = 0, SYG_WINDOW_HAMMING = 1, SYG_WINDOW_BLACKMAN = 2, SYG_WINDOW_BOXCAR = 3 };
@@ -105,6 +109,8 @@ typedef struct {
     double contrast_quantile; /* 0.02 (double: rint(quantile * n_bins) must round as numpy does) */
     /* feature_params['spectral_rolloff'] (frequency_domain.py:277) */
     double roll_percent;      /* 0.85 */
+    /* feature_params['signal_entropy'] (time_domain.py:186) */
+    int32_t entropy_bins;     /* 10; supported range 1..16 */
 } syg_feature_params;
 
 const char* syg_version(void);

@@ -303,9 +303,42 @@ def mfcc(y=None, sr=None, S=None, n_mfcc=13, dct_type=2, norm="ortho", lifter=0.
 # ----------------------------------------------------------------------------
 # manager.py:78-445
 # ----------------------------------------------------------------------------
+def skewness(frame):
+    """time_domain.py:67-97"""
+    import scipy.stats
+    if frame.size < 2:
+        return np.float64(0.0)
+    if np.var(frame) < _EPSILON:
+        return np.float64(0.0)
+    return np.float64(scipy.stats.skew(frame, bias=False))
+
+
+def kurtosis_val(frame):
+    """time_domain.py:99-126"""
+    import scipy.stats
+    if frame.size < 4:
+        return np.float64(0.0)
+    if np.var(frame) < _EPSILON:
+        return np.float64(0.0)
+    return np.float64(scipy.stats.kurtosis(frame, fisher=True, bias=False))
+
+
+def signal_entropy(frame, num_bins=10):
+    """time_domain.py:186-227"""
+    import scipy.stats
+    if frame.size < 2 or num_bins < 1:
+        return np.float64(0.0)
+    if np.all(frame == frame[0]):
+        return np.float64(0.0)
+    counts, _ = np.histogram(frame, bins=num_bins, density=False)
+    pk = counts[counts > 0] / frame.size
+    return np.float64(scipy.stats.entropy(pk))
+
+
 _PER_FRAME_TIME = {
     "peak_amplitude": peak_amplitude, "crest_factor": crest_factor,
     "mean_amplitude": mean_amplitude, "std_dev_amplitude": std_dev_amplitude,
+    "skewness": skewness, "kurtosis": kurtosis_val, "signal_entropy": signal_entropy,
 }
 _PER_FRAME_SPEC = {
     "spectral_centroid": spectral_centroid, "spectral_rolloff": spectral_rolloff,
@@ -390,7 +423,9 @@ def extract_features(y, sr, features, frame_length=2048, hop_length=512, center=
                 if fr.shape[1] > cur:
                     fr = fr[:, :cur]
                 fn = _PER_FRAME_TIME[name]
-                out.append((name, np.array([fn(fr[:, i]) for i in range(fr.shape[1])], dtype=np.float64)))
+                import inspect
+                kw = {k: v for k, v in params.items() if k in inspect.signature(fn).parameters}   # :283 user params only
+                out.append((name, np.array([fn(fr[:, i], **kw) for i in range(fr.shape[1])], dtype=np.float64)))
             elif name in _PER_FRAME_SPEC:                                        # :289-319
                 S, f = get_mag()
                 cur = S.shape[1]

@@ -31,6 +31,10 @@ FEATURE_IDS = {
     "dominant_frequency": 9,
     "mean_amplitude": 10,
     "std_dev_amplitude": 11,
+    "zero_crossing_rate": 12,
+    "skewness": 13,
+    "kurtosis": 14,
+    "signal_entropy": 15,
 }
 WINDOW_IDS = {"hann": 0, "hanning": 0, "hamming": 1, "blackman": 2, "boxcar": 3, "rectangular": 3, "rect": 3, "ones": 3}
 PAD_IDS = {"constant": 0, "reflect": 1}
@@ -55,7 +59,7 @@ class SygFeatureParams(C.Structure):
                 ("n_mels", C.c_int32), ("fmin", C.c_double), ("fmax", C.c_double), ("power", C.c_double),
                 ("n_mfcc", C.c_int32), ("dct_type", C.c_int32), ("dct_ortho", C.c_int32), ("lifter", C.c_double),
                 ("contrast_n_bands", C.c_int32), ("contrast_fmin", C.c_double), ("contrast_quantile", C.c_double),
-                ("roll_percent", C.c_double)]
+                ("roll_percent", C.c_double), ("entropy_bins", C.c_int32)]
 
 
 def default_library_path() -> str:
@@ -233,6 +237,7 @@ def make_params(lib: Library, sr: int, features: Sequence[str], frame_length: in
     p.contrast_quantile = float(c.get("quantile", 0.02))
     r = fp.get("spectral_rolloff", {})
     p.roll_percent = float(r.get("roll_percent", 0.85))
+    p.entropy_bins = int(fp.get("signal_entropy", {}).get("num_bins", 10))
     return p
 
 

@@ -225,6 +225,7 @@ struct FeaturePlan {
     size_t ws_per_unit = 0;        // bytes of melws + cws (+ spectra when two-stage) per unit
     bool two_stage = false;        // warp kernel as FFT launch + epilogue launch (spectra through an L2-sized workspace)
     int n_fft = 0;
+    int entropy_bins = 10;
 };
 
 int rows_of(const syg_feature_params* p, int32_t* n_rows) {
@@ -259,7 +260,7 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
     std::memset(&pl.fin, 0, sizeof(pl.fin));
     syg::FrameArgs& a = pl.fa;
     a.row_centroid = a.row_rolloff = a.row_rms = a.row_crest = a.row_peak = a.row_bandwidth = a.row_flatness =
-        a.row_dominant = a.row_zcr = a.row_mean_amp = a.row_std_amp = -1;
+        a.row_dominant = a.row_zcr = a.row_mean_amp = a.row_std_amp = a.row_skew = a.row_kurt = a.row_entropy = -1;
     pl.fin.row_mfcc = -1;
     pl.fin.row_contrast = -1;
     int row = 0;
@@ -278,6 +279,10 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
             case SYG_FEAT_DOMINANT_FREQUENCY: mask |= syg::FB_DOMINANT; a.row_dominant = row++; break;
             case SYG_FEAT_MEAN_AMPLITUDE: mask |= syg::FB_MEAN_AMP; a.row_mean_amp = row++; break;
             case SYG_FEAT_STD_DEV_AMPLITUDE: mask |= syg::FB_STD_AMP; a.row_std_amp = row++; break;
+            case SYG_FEAT_ZERO_CROSSING_RATE: mask |= syg::FB_ZCR; a.row_zcr = row++; break;
+            case SYG_FEAT_SKEWNESS: mask |= syg::FB_SKEW; a.row_skew = row++; break;
+            case SYG_FEAT_KURTOSIS: mask |= syg::FB_KURT; a.row_kurt = row++; break;
+            case SYG_FEAT_SIGNAL_ENTROPY: mask |= syg::FB_ENTROPY; a.row_entropy = row++; break;
         }
     }
     a.mask = mask;
@@ -359,6 +364,9 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         ws += (size_t)T * 2 * b.nb * sizeof(float);
     }
     pl.n_fft = fl;
+    pl.entropy_bins = p->entropy_bins;
+    if ((mask & syg::FB_ENTROPY) && (p->entropy_bins < 1 || p->entropy_bins > 16))
+        return fail(SYG_E_UNSUPPORTED, "signal_entropy num_bins=%d: supported range is [1, 16]", p->entropy_bins);
     {
         // two-stage launch: worth it when the epilogues dominate (they are latency bound and run at twice the occupancy on
         // their own); SYGB200_TWO_STAGE=0/1 overrides
@@ -397,7 +405,14 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
     a.pws = reinterpret_cast<float*>(w + off);
     const bool need_fin = (a.mask & (syg::FB_MFCC | syg::FB_CONTRAST)) != 0;
     if (need_fin) CK(cudaMemsetAsync(a.unit_max, 0, (size_t)g.n_units * 4 * sizeof(unsigned), st));
-    int rc;
+    int rc = SYG_OK;
+    if (a.mask & syg::FB_TIME_EXTRA) {                                  // zcr / skewness / kurtosis / entropy: their own streaming kernel
+        std::string err;
+        ProfScope ps(ctx, st, PROF_FRAME);
+        const int trc = syglaunch::time_extra(a, n_fft, pl.entropy_bins, ctx->sm_count, st, err);
+        if (trc) return fail(trc, "%s", err.c_str());
+    }
+    if ((a.mask & ~syg::FB_TIME_EXTRA) == 0) return SYG_OK;             // nothing for the frame kernels
     if (pl.two_stage) {
         {
             ProfScope ps(ctx, st, PROF_FRAME);
@@ -746,6 +761,7 @@ void syg_feature_params_default(syg_feature_params* p) {
     p->contrast_fmin = 200.0;
     p->contrast_quantile = 0.02;
     p->roll_percent = 0.85;      // frequency_domain.py:277
+    p->entropy_bins = 10;         // time_domain.py:186
 }
 
 int syg_features_rows(const syg_feature_params* p, int32_t* n_rows) { return rows_of(p, n_rows); }

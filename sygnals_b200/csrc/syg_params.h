@@ -16,11 +16,12 @@ namespace syg {
 enum : unsigned {
     FB_MFCC = 1u << 0, FB_CONTRAST = 1u << 1, FB_CENTROID = 1u << 2, FB_ROLLOFF = 1u << 3, FB_RMS = 1u << 4,
     FB_CREST = 1u << 5, FB_PEAK = 1u << 6, FB_BANDWIDTH = 1u << 7, FB_FLATNESS = 1u << 8, FB_DOMINANT = 1u << 9,
-    FB_ZCR = 1u << 10, FB_MEAN_AMP = 1u << 11, FB_STD_AMP = 1u << 12,
+    FB_ZCR = 1u << 10, FB_MEAN_AMP = 1u << 11, FB_STD_AMP = 1u << 12, FB_SKEW = 1u << 13, FB_KURT = 1u << 14, FB_ENTROPY = 1u << 15,
 };
 constexpr unsigned FB_SPECTRUM_ANY = FB_MFCC | FB_CONTRAST | FB_CENTROID | FB_ROLLOFF | FB_BANDWIDTH | FB_FLATNESS | FB_DOMINANT;
 constexpr unsigned FB_SPECSTATS = FB_CENTROID | FB_ROLLOFF | FB_BANDWIDTH | FB_FLATNESS | FB_DOMINANT;
-constexpr unsigned FB_TIME_ANY = FB_RMS | FB_CREST | FB_PEAK | FB_ZCR | FB_MEAN_AMP | FB_STD_AMP;
+constexpr unsigned FB_TIME_ANY = FB_RMS | FB_CREST | FB_PEAK | FB_MEAN_AMP | FB_STD_AMP;            // time features of the frame kernels
+constexpr unsigned FB_TIME_EXTRA = FB_ZCR | FB_SKEW | FB_KURT | FB_ENTROPY;                           // time_extra_kernel
 
 constexpr int kMaxBands = 12;   // spectral-contrast bands incl. the top one (n_bands + 1)
 
@@ -66,7 +67,7 @@ struct FrameArgs {
     int band_n[kMaxBands];      // quantile count
     // per-frame rows written directly (row < 0: not requested)
     int row_centroid, row_rolloff, row_rms, row_crest, row_peak, row_bandwidth, row_flatness, row_dominant,
-        row_zcr, row_mean_amp, row_std_amp;
+        row_zcr, row_mean_amp, row_std_amp, row_skew, row_kurt, row_entropy;
     int n_rows;
     float* out;                 // [n_units][n_rows][T]
     float* melws;               // [n_frames][n_mels]   raw mel energies

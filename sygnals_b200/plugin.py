@@ -11,7 +11,7 @@ looked up, ``sygnals/core/data_handler.py:126,223``) and the CLI binds the hot-p
 attributes to the engine's mirrors (``sygnals_b200.core``) and ``teardown()`` restores them.
 
 Routing rule (no CPU fallback inside the engine): a call is served by the engine when every requested feature has a CUDA
-kernel and the frame geometry is supported; anything else (pitch/HNR/jitter/shimmer, zero-crossing rate, non power-of-two
+kernel and the frame geometry is supported; anything else (pitch/HNR/jitter/shimmer, non power-of-two
 ``frame_length``, exotic windows) is handed to the ORIGINAL reference function untouched -- those features "stay on the
 reference path" exactly as the scope contract says.  Configure with ``[plugins.sygnals-b200]`` in the Sygnals
 config: ``device`` (int, default LOCAL_RANK or 0), ``rebind`` (bool, default true), ``strict`` (bool, default false: raise

@@ -13,7 +13,7 @@ needs_ref = pytest.mark.skipif(not ref_loader.reference_available(), reason="/ro
 
 FEATS = ["mfcc", "spectral_contrast", "spectral_centroid", "spectral_rolloff", "rms_energy", "crest_factor",
          "zero_crossing_rate", "spectral_bandwidth", "spectral_flatness", "dominant_frequency", "peak_amplitude",
-         "mean_amplitude", "std_dev_amplitude"]
+         "mean_amplitude", "std_dev_amplitude", "skewness", "kurtosis", "signal_entropy"]
 
 
 @needs_ref
@@ -28,7 +28,8 @@ def test_extract_features_equals_reference(sr, L, fl, hop):
         rng = np.random.default_rng(L + fl)
         t = np.arange(L) / sr
         y = (0.4 * np.sin(2 * np.pi * 440 * t) + 0.05 * rng.standard_normal(L)).astype(np.float32).astype(np.float64)
-        fp = {"mfcc": {"n_mels": 64, "n_mfcc": 16, "lifter": 22.0}, "spectral_rolloff": {"roll_percent": 0.9}}
+        fp = {"mfcc": {"n_mels": 64, "n_mfcc": 16, "lifter": 22.0}, "spectral_rolloff": {"roll_percent": 0.9},
+              "signal_entropy": {"num_bins": 12}}
         a = extract_features(y, sr, FEATS, frame_length=fl, hop_length=hop, feature_params=fp,
                              output_format="dict_of_arrays")
         b = O.extract_features(y, sr, FEATS, frame_length=fl, hop_length=hop, feature_params=fp)

@@ -71,6 +71,12 @@ def check_rows(names, got, ref, bin_hz=None, nyq=None, contrast_ok=None):
             off = d / bin_hz
             assert off.max() <= 1.0 + 1e-6, f"{n}: off by {off.max():.2f} bins"
             assert (off > 0.5).mean() <= 1e-3, f"{n}: {(off > 0.5).sum()} of {off.size} frames differ"
+        elif n == "zero_crossing_rate":
+            assert np.array_equal(g, r.astype(np.float32)), f"{n}: differs on {(g != r.astype(np.float32)).sum()} frames"   # counts / frame_length
+        elif n in ("skewness", "kurtosis"):
+            assert (d <= 2e-5 * np.abs(r) + 2e-6).all(), f"{n}: worst {d.max():.3e}"
+        elif n == "signal_entropy":
+            assert (d <= 1e-6).all(), f"{n}: worst {d.max():.3e}"
         elif n == "spectral_bandwidth":
             assert (d <= 1e-4 * np.abs(r) + 1e-2).all(), f"{n}: worst {d.max():.3e}"
         elif n == "spectral_flatness":
@@ -386,3 +392,30 @@ def test_segment_aggregation_vs_oracle(eng, agg):
         d = {n: cube[s, j].astype(np.float64) for j, n in enumerate(names)}
         r = orc.format_feature_vectors_per_segment(d, [(0, T)], aggregation)[0]
         np.testing.assert_allclose(got2[s], r, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("sr,fl,hop,n,center", [(22050, 1024, 256, 6000, True), (16000, 512, 160, 3001, True), (44100, 2048, 512, 9000, False),
+                                               (8000, 64, 16, 700, True), (48000, 4096, 1024, 20000, True)])
+def test_time_extra_features_vs_oracle(eng, sr, fl, hop, n, center):
+    """zero_crossing_rate (edge padding), skewness, kurtosis, signal_entropy (time_extra_kernel) alone and mixed with kernel features."""
+    y = synth.long_signal(n, sr, seed=fl + n, block_sec=0.05)        # silent, DC and noisy blocks: flat frames, ties at bin edges
+    feats = ["zero_crossing_rate", "skewness", "rms_energy", "kurtosis", "signal_entropy", "spectral_centroid"]
+    fp = {"signal_entropy": {"num_bins": 12}} if fl == 512 else None
+    names, ref = oracle_rows(y, sr, feats, fl, hop, fp, center=center)
+    p = _ffi.make_params(eng.lib, sr, feats, fl, hop, center=center, feature_params=fp)
+    out = eng.features_host(y, eng.units_clips(1, n), p)
+    assert out.shape == (1,) + ref.shape
+    check_rows(names, out[0], ref, bin_hz=sr / fl)
+    only = ["skewness", "zero_crossing_rate"]                        # no frame-kernel feature at all
+    names2, ref2 = oracle_rows(y, sr, only, fl, hop, None, center=center)
+    out2 = eng.features_host(y, eng.units_clips(1, n), _ffi.make_params(eng.lib, sr, only, fl, hop, center=center))
+    check_rows(names2, out2[0], ref2, bin_hz=sr / fl)
+    # padded units: the zero tail is part of the unit (zcr's edge value is then 0), three units per call
+    u = eng.units_clips(3, n // 2, total_len=n, stride=n // 3)
+    out3 = eng.features_host(y, u, p)
+    for i in range(3):
+        seg = np.zeros(n // 2, dtype=np.float32)
+        v = max(0, min(n // 2, n - i * (n // 3)))
+        seg[:v] = y[i * (n // 3): i * (n // 3) + v]
+        _, r3 = oracle_rows(seg, sr, feats, fl, hop, fp, center=center)
+        check_rows(names, out3[i], r3, bin_hz=sr / fl)
