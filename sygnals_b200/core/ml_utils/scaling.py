@@ -1,0 +1,124 @@
+"""Sharded counterpart of ``sygnals/core/ml_utils/scaling.py:49-175`` (``apply_scaling`` with the ``'standard'`` and ``'minmax'``
+scalers of scikit-learn) for the feature matrix the engine produces: every rank holds a block of rows ``[n_local, n_features]``
+(``dist.segment_features_sharded(..., aggregation=...)`` without the final gather), the column statistics are one
+``all_reduce`` of (count, sum, sum of squares) or (min, max), and the transform is applied where the rows live.
+
+The fitted object carries scikit-learn's attribute names (``mean_``, ``var_``, ``scale_``, ``n_samples_seen_`` /
+``data_min_``, ``data_max_``, ``data_range_``, ``scale_``, ``min_``) so it can stand in for ``apply_scaling``'s second return
+value; NaNs are ignored in ``fit`` and kept in ``transform`` exactly as scikit-learn does.  torch tensors (CUDA -> NCCL, CPU ->
+gloo) or numpy arrays.  ``'robust'`` (medians/quantiles over the whole column) stays on the reference path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+@dataclass
+class FittedScaler:
+    kind: str
+    n_samples_seen_: np.ndarray
+    scale_: np.ndarray
+    mean_: Optional[np.ndarray] = None          # standard
+    var_: Optional[np.ndarray] = None
+    with_mean: bool = True
+    with_std: bool = True
+    data_min_: Optional[np.ndarray] = None      # minmax
+    data_max_: Optional[np.ndarray] = None
+    data_range_: Optional[np.ndarray] = None
+    min_: Optional[np.ndarray] = None
+    feature_range: Tuple[float, float] = (0.0, 1.0)
+    _dev: dict = field(default_factory=dict, repr=False)
+
+    def transform(self, X):
+        is_np = isinstance(X, np.ndarray)
+        if is_np:
+            if self.kind == "standard":
+                out = X.astype(np.float64, copy=True)
+                if self.with_mean:
+                    out -= self.mean_
+                if self.with_std:
+                    out /= self.scale_
+                return out
+            return X.astype(np.float64) * self.scale_ + self.min_
+        import torch
+        key = (X.device, X.dtype)
+        if key not in self._dev:
+            t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float64, device=X.device)  # noqa: E731
+            self._dev[key] = (t(self.mean_), t(self.scale_), t(self.min_))
+        mean, scale, mn = self._dev[key]
+        Xd = X.to(torch.float64)
+        if self.kind == "standard":
+            if self.with_mean:
+                Xd = Xd - mean
+            return Xd / scale if self.with_std else Xd
+        return Xd * scale + mn
+
+
+def _handle_zeros(scale: np.ndarray) -> np.ndarray:
+    """sklearn.preprocessing._data._handle_zeros_in_scale: (near-)constant columns are left unscaled."""
+    s = scale.copy()
+    s[s < 10 * np.finfo(np.float64).eps] = 1.0
+    return s
+
+
+def fit_scaler(X_local, scaler_type: str = "standard", with_mean: bool = True, with_std: bool = True,
+               feature_range: Tuple[float, float] = (0.0, 1.0), group=None) -> FittedScaler:
+    """Column statistics over ALL ranks' rows (one all-reduce when a process group is initialised)."""
+    import torch
+    import torch.distributed as dist
+    if scaler_type not in ("standard", "minmax"):
+        raise NotImplementedError(f"scaler_type={scaler_type!r}: the sharded engine fits 'standard' and 'minmax' "
+                                  "('robust' needs column medians over all rows and stays on the reference path)")
+    X = torch.as_tensor(X_local)
+    if X.dim() == 1:
+        X = X.reshape(-1, 1)
+    if X.dim() != 2:
+        raise ValueError(f"Input features must be 1D or 2D (samples/frames x features), got shape {tuple(X.shape)}")
+    X = X.to(torch.float64)
+    nan = torch.isnan(X)
+    world = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if scaler_type == "standard":
+        Z = torch.where(nan, torch.zeros_like(X), X)
+        stats = torch.stack([(~nan).sum(0).to(torch.float64), Z.sum(0)])
+        if world:
+            dist.all_reduce(stats, group=group)
+        n = stats[0]
+        mean = stats[1] / n
+        # second pass around the global mean (no cancellation), second all-reduce of one row
+        ss = torch.where(nan, torch.zeros_like(X), (X - mean) ** 2).sum(0)
+        if world:
+            dist.all_reduce(ss, group=group)
+        var = (ss / n).cpu().numpy()
+        scale = _handle_zeros(np.sqrt(var)) if with_std else np.ones_like(var)
+        return FittedScaler("standard", n.cpu().numpy().astype(np.int64), scale, mean_=mean.cpu().numpy(), var_=var,
+                            with_mean=with_mean, with_std=with_std)
+    big = torch.finfo(torch.float64).max
+    mn = torch.where(nan, torch.full_like(X, big), X).amin(0) if X.shape[0] else torch.full((X.shape[1],), big, dtype=torch.float64, device=X.device)
+    mx = torch.where(nan, torch.full_like(X, -big), X).amax(0) if X.shape[0] else torch.full((X.shape[1],), -big, dtype=torch.float64, device=X.device)
+    cnt = (~nan).sum(0).to(torch.float64)
+    if world:
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(cnt, group=group)
+    dmin, dmax = mn.cpu().numpy(), mx.cpu().numpy()
+    rng = dmax - dmin
+    lo, hi = feature_range
+    scale = (hi - lo) / _handle_zeros(rng)
+    return FittedScaler("minmax", cnt.cpu().numpy().astype(np.int64), scale, data_min_=dmin, data_max_=dmax, data_range_=rng,
+                        min_=lo - dmin * scale, feature_range=(lo, hi))
+
+
+def apply_scaling(features, scaler_type: str = "standard", scaler_params: Optional[dict] = None, fit: bool = True,
+                  scaler_instance: Optional[FittedScaler] = None, group=None):
+    """Mirror of ``apply_scaling`` (scaling.py:49-142) on this rank's block of rows: (scaled block, fitted scaler)."""
+    if fit:
+        sc = fit_scaler(features, scaler_type, group=group, **(scaler_params or {}))
+    else:
+        if scaler_instance is None:
+            raise ValueError("`scaler_instance` must be provided when `fit=False`.")
+        sc = scaler_instance
+    X = features.reshape(-1, 1) if getattr(features, "ndim", 2) == 1 else features
+    return sc.transform(X), sc

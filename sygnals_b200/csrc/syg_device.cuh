@@ -449,8 +449,7 @@ SYG_DEVICE SYG_INLINE float warp_extreme_mean_sqrt(const float* p, int lo, int c
 }
 
 // --------------------------------------------------------------------------------------------------------
-// register-resident selection for spectral contrast (warp kernel).  Keys are the bit images of non-negative
-// floats (order preserving as unsigned).
+// hardware square root (flush-to-zero: a denormal |X|^2 is silence)
 // --------------------------------------------------------------------------------------------------------
 SYG_DEVICE SYG_INLINE float sqrt_approx(float x) {
 #if defined(SYG_EMU)
@@ -462,206 +461,8 @@ SYG_DEVICE SYG_INLINE float sqrt_approx(float x) {
 #endif
 }
 
-// full-warp bitonic sort of unsigned keys, descending by lane (one out-of-line copy: code size matters more than the call)
-SYG_DEVICE SYG_NOINLINE unsigned warp_sort_desc_u(unsigned v) {
-    const int lane = threadIdx.x & 31;
-    SYG_UNROLL
-    for (int k = 2; k <= 32; k <<= 1) {
-        SYG_UNROLL
-        for (int jj = k >> 1; jj > 0; jj >>= 1) {
-            const unsigned o = __shfl_xor_sync(kFull, v, jj);
-            const bool desc = ((lane & k) == 0);
-            const bool lower = ((lane & jj) == 0);
-            v = (lower == desc) ? max(v, o) : min(v, o);
-        }
-    }
-    return v;
-}
-
-// Sum of sqrt(value) over the n largest of <= 32 candidate keys (one per lane, lanes >= c hold nothing), where
-// value = float(key ^ flip).  c >= n.
-SYG_DEVICE SYG_NOINLINE float warp_top_of_candidates(unsigned k, int c, int n, unsigned flip) {
-    const int lane = threadIdx.x & 31;
-    int extra = c - n;                               // drop the `extra` smallest candidates
-    if (extra <= 8) {
-        unsigned km = (lane < c) ? k : 0xffffffffu;
-        for (; extra > 0; --extra) {
-            const unsigned g = __reduce_min_sync(kFull, km);
-            const unsigned b = __ballot_sync(kFull, km == g);
-            if (lane == __ffs(b) - 1) km = 0xffffffffu;
-        }
-        const float contrib = (km != 0xffffffffu) ? sqrt_approx(__uint_as_float(km ^ flip)) : 0.0f;
-        return warp_sum(contrib);
-    }
-    k = warp_sort_desc_u((lane < c) ? k : 0u);
-    const float contrib = (lane < n) ? sqrt_approx(__uint_as_float(k ^ flip)) : 0.0f;
-    return warp_sum(contrib);
-}
-
-// n-th largest of the 32 lane values (n <= 32), or 0 if fewer than n lanes hold a non-zero key
-SYG_DEVICE SYG_NOINLINE unsigned warp_nth_largest(unsigned lm, unsigned top, int n) {
-    if (n > 6) {
-        const unsigned srt = warp_sort_desc_u(lm);
-        return __shfl_sync(kFull, srt, n - 1);
-    }
-    unsigned k = lm, g = top;
-    int removed = 0;
-    for (;;) {
-        const unsigned b = __ballot_sync(kFull, k == g);
-        removed += __popc(b);
-        if (removed >= n) break;
-        if (k == g) k = 0u;
-        g = __reduce_max_sync(kFull, k);
-        if (g == 0u) break;
-    }
-    return g;
-}
-
-// Sum over the n largest of the warp's keys kd[i] (i < V, entries with i >= nv are absent) of sqrt(value), where
-// value = float(key ^ flip).  Exact (ties only enter through their value); returns < 0 when the caller must take the
-// slow path (more than 32 candidates, or n > 32).  cand: 32 unsigned of warp-private shared memory.
-template <int V>
-SYG_DEVICE SYG_INLINE float warp_top_sqrt_sum(const unsigned (&kd)[V], int n, unsigned flip, unsigned* cand) {
-    // absent entries hold key 0: they can only be selected when thr == 0, which overflows cand[] -> slow path
-    const int lane = threadIdx.x & 31;
-    unsigned lm = 0u;
-    SYG_UNROLL
-    for (int i = 0; i < V; ++i) lm = max(lm, kd[i]);
-    const unsigned top = __reduce_max_sync(kFull, lm);
-    if (n == 1) return sqrt_approx(__uint_as_float(top ^ flip));
-    if (n > 32) return -1.0f;
-    const unsigned thr = warp_nth_largest(lm, top, n);
-    if (thr == top) return (float)n * sqrt_approx(__uint_as_float(top ^ flip));      // the n largest are all equal
-    // compact the candidates (>= thr; typically n .. 2n of them) into cand[0..31]; cand[32] is the counter
-    if (lane == 0) cand[32] = 0u;
-    __syncwarp();
-    SYG_UNROLL
-    for (int i = 0; i < V; ++i) {
-        if (kd[i] >= thr) {
-            const unsigned slot = atomicAdd(&cand[32], 1u);
-            if (slot < 32u) cand[slot] = kd[i];
-        }
-    }
-    __syncwarp();
-    const int c = (int)cand[32];
-    if (c > 32) return -1.0f;
-    const unsigned k = (lane < c) ? cand[lane] : 0u;
-    __syncwarp();
-    return warp_top_of_candidates(k, c, n, flip);
-}
-
-// Exact slow path: sum of sqrt of the n largest (inv: smallest) of p[padi(lo + i)], i < count, by a bitwise search for
-// the n-th largest key over shared memory.  Rare (more than 32 candidates tie-close to the threshold, or n > 32).
-SYG_DEVICE SYG_NOINLINE float band_select_slow(const float* __restrict__ p, int lo, int count, int n, bool inv) {
-    const int lane = threadIdx.x & 31;
-    const unsigned flip = inv ? 0xffffffffu : 0u;
-    unsigned prefix = 0u;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-    for (int bit = 31; bit >= 0; --bit) {
-        const unsigned trial = prefix | (1u << bit);
-        int cnt = 0;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-        for (int i = lane; i < count; i += 32) cnt += ((__float_as_uint(p[padi(lo + i)]) ^ flip) >= trial) ? 1 : 0;
-        cnt = __reduce_add_sync(kFull, cnt);
-        if (cnt >= n) prefix = trial;
-    }
-    float s_gt = 0.0f;
-    int c_gt = 0;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-    for (int i = lane; i < count; i += 32) {
-        const unsigned k = __float_as_uint(p[padi(lo + i)]) ^ flip;
-        if (k > prefix) { s_gt += sqrt_approx(__uint_as_float(k ^ flip)); c_gt++; }
-    }
-    s_gt = warp_sum(s_gt);
-    c_gt = __reduce_add_sync(kFull, c_gt);
-    return s_gt + (float)(n - c_gt) * sqrt_approx(__uint_as_float(prefix ^ flip));
-}
-
-// peak / valley (mean magnitude of the n largest / n smallest |X|^2 bins) of the band [lo, lo + count) of one frame's
-// padded power spectrum p.  V * 32 >= count.
-template <int V>
-SYG_DEVICE SYG_INLINE void band_extremes(const float* __restrict__ p, int lo, int count, int n, unsigned* cand,
-                                         float& peak, float& valley) {
-    const int lane = threadIdx.x & 31;
-    if (n > count) n = count;
-    const float* q = p + padi(lo + lane);            // element i of this lane: q[33 * i]
-    int nv = (count - lane + 31) >> 5;               // valid elements of this lane
-    if (nv < 0) nv = 0;
-    unsigned kd[V];
-    SYG_UNROLL
-    for (int i = 0; i < V; ++i) kd[i] = (i < nv) ? __float_as_uint(q[33 * i]) : 0u;
-    const float inv_n = 1.0f / (float)n;
-    float sp = 0.0f, sv = 0.0f;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-    for (int dir = 0; dir < 2; ++dir) {               // 0: largest, 1: smallest (keys complemented)
-        const unsigned flip = dir ? 0xffffffffu : 0u;
-        if (dir) {
-            SYG_UNROLL
-            for (int i = 0; i < V; ++i) kd[i] = (i < nv) ? ~kd[i] : 0u;
-        }
-        float r = warp_top_sqrt_sum<V>(kd, n, flip, cand);
-        if (r < 0.0f) r = band_select_slow(p, lo, count, n, dir != 0);
-        if (dir) sv = r; else sp = r;
-    }
-    peak = sp * inv_n;
-    valley = sv * inv_n;
-}
-
-// small bands with small n (the lower octave bands): repeated extraction of the maximum straight from registers
-template <int V>
-SYG_DEVICE SYG_INLINE void band_extremes_small(const float* __restrict__ p, int lo, int count, int n, float& peak, float& valley) {
-    const int lane = threadIdx.x & 31;
-    const float* q = p + padi(lo + lane);
-    int nv = (count - lane + 31) >> 5;
-    if (nv < 0) nv = 0;
-    unsigned k0[V];
-    SYG_UNROLL
-    for (int i = 0; i < V; ++i) k0[i] = (i < nv) ? __float_as_uint(q[33 * i]) : 0u;
-    float res[2];
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-    for (int dir = 0; dir < 2; ++dir) {
-        const unsigned flip = dir ? 0xffffffffu : 0u;
-        unsigned kd[V];
-        SYG_UNROLL
-        for (int i = 0; i < V; ++i) kd[i] = (i < nv) ? (k0[i] ^ flip) : 0u;
-        float sum = 0.0f;
-        for (int it = 0; it < n; ++it) {
-            unsigned lm = 0u;
-            SYG_UNROLL
-            for (int i = 0; i < V; ++i) lm = max(lm, kd[i]);
-            const unsigned g = __reduce_max_sync(kFull, lm);
-            sum += sqrt_approx(__uint_as_float(g ^ flip));
-            const unsigned b = __ballot_sync(kFull, lm == g);
-            if (lane == __ffs(b) - 1) {                 // the owner drops one instance of g
-                bool done = false;
-                SYG_UNROLL
-                for (int i = 0; i < V; ++i) {
-                    const bool hit = !done && kd[i] == g;
-                    if (hit) kd[i] = 0u;
-                    done = done || hit;
-                }
-            }
-        }
-        res[dir] = sum;
-    }
-    const float inv_n = 1.0f / (float)n;
-    peak = res[0] * inv_n;
-    valley = res[1] * inv_n;
-}
-
 // --------------------------------------------------------------------------------------------------------
-// warp kernel, second generation of the spectral-contrast selection (everything in registers, no shared-memory
-// candidate list).  P spectra of the warp kernel use 4 pad words per 32 bins:
+// warp kernel: spectral-contrast selection (everything in registers).  P spectra of the warp kernel use 4 pad words per 32 bins:
 // --------------------------------------------------------------------------------------------------------
 SYG_DEVICE SYG_INLINE int ppad(int k) { return k + ((k >> 5) << 2); }
 
@@ -866,39 +667,6 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
     return r;
 }
 
-// exact fallback for bands the register path does not cover (more than 1024 bins, or n > 32): bitwise search for the
-// n-th largest key over shared memory (ppad layout)
-SYG_DEVICE SYG_NOINLINE float band_select_slow36(const float* __restrict__ p, int lo, int count, int n, bool inv) {
-    const int lane = threadIdx.x & 31;
-    const unsigned flip = inv ? 0xffffffffu : 0u;
-    unsigned prefix = 0u;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-    for (int bit = 31; bit >= 0; --bit) {
-        const unsigned trial = prefix | (1u << bit);
-        int cnt = 0;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-        for (int i = lane; i < count; i += 32) cnt += ((__float_as_uint(p[ppad(lo + i)]) ^ flip) >= trial) ? 1 : 0;
-        cnt = __reduce_add_sync(kFull, cnt);
-        if (cnt >= n) prefix = trial;
-    }
-    float s_gt = 0.0f;
-    int c_gt = 0;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-    for (int i = lane; i < count; i += 32) {
-        const unsigned k = __float_as_uint(p[ppad(lo + i)]) ^ flip;
-        if (k > prefix) { s_gt += sqrt_approx(__uint_as_float(k ^ flip)); c_gt++; }
-    }
-    s_gt = warp_sum(s_gt);
-    c_gt = __reduce_add_sync(kFull, c_gt);
-    return s_gt + (float)(n - c_gt) * sqrt_approx(__uint_as_float(prefix ^ flip));
-}
-
 SYG_DEVICE SYG_INLINE void band_peak_valley_any(const float* __restrict__ p, int lo, int count, int n, float& peak, float& valley) {
     if (count <= 0) { peak = valley = __uint_as_float(0x7fc00000u); return; }     // mean of nothing -> NaN (numpy)
     if (n > count) n = count;
@@ -906,31 +674,6 @@ SYG_DEVICE SYG_INLINE void band_peak_valley_any(const float* __restrict__ p, int
     const float2 r = band_peak_valley_stream(p, lo, count, n);
     peak = r.x;
     valley = r.y;
-}
-
-SYG_DEVICE SYG_NOINLINE void band_extremes_any(const float* __restrict__ p, int lo, int count, int n, unsigned* cand,
-                                               float& peak, float& valley) {
-    if (count <= 0) { peak = valley = __uint_as_float(0x7fc00000u); return; }     // mean of nothing -> NaN (numpy)
-    if (n > count) n = count;
-    if (n == 1) {                                       // extremes of the band
-        const int lane = threadIdx.x & 31;
-        unsigned mx = 0u, mn = 0xffffffffu;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-        for (int i = lane; i < count; i += 32) {
-            const unsigned k = __float_as_uint(p[padi(lo + i)]);
-            mx = max(mx, k);
-            mn = min(mn, k);
-        }
-        peak = sqrt_approx(__uint_as_float(__reduce_max_sync(kFull, mx)));
-        valley = sqrt_approx(__uint_as_float(__reduce_min_sync(kFull, mn)));
-        return;
-    }
-    if (count <= 192 && n <= 4) band_extremes_small<6>(p, lo, count, n, peak, valley);
-    else if (count <= 192) band_extremes<6>(p, lo, count, n, cand, peak, valley);
-    else if (count <= 768) band_extremes<24>(p, lo, count, n, cand, peak, valley);
-    else band_extremes<33>(p, lo, count, n, cand, peak, valley);
 }
 
 }  // namespace sygdev

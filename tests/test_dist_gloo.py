@@ -88,3 +88,55 @@ def test_two_rank_gloo_gather_equals_single_rank():
     for rank, names, feats, _ in got:
         assert names == one["names"]
         np.testing.assert_array_equal(feats, one["features"])       # same kernels, same units -> bit-identical after gather
+
+
+def _scaler_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from sygnals_b200.core.ml_utils import scaling
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X = _scaler_matrix()
+        a, b = sdist.shard_range(X.shape[0], rank, world)
+        res = {}
+        for kind, params in (("standard", {}), ("minmax", {"feature_range": (-1.0, 2.0)})):
+            Y, sc = scaling.apply_scaling(torch.from_numpy(X[a:b]), kind, params)
+            res[kind] = (Y.numpy(), sc.scale_, sc.mean_ if kind == "standard" else sc.min_)
+        q.put((rank, a, b, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def _scaler_matrix():
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((101, 6)) * np.array([1.0, 10.0, 1e-3, 5.0, 1.0, 2.0]) + np.array([0.0, 3.0, 1.0, -2.0, 7.0, 0.0])
+    X[:, 4] = 7.0                                   # constant column -> scale 1 (sklearn _handle_zeros_in_scale)
+    X[rng.integers(0, 101, 9), 1] = np.nan          # NaNs are ignored in fit, kept in transform
+    return X
+
+
+def test_sharded_scaler_equals_sklearn_two_ranks():
+    import torch.multiprocessing as mp
+    from sklearn.preprocessing import MinMaxScaler, StandardScaler
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_scaler_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=240) for _ in procs], key=lambda g: g[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X = _scaler_matrix()
+    ref = {"standard": StandardScaler().fit(X), "minmax": MinMaxScaler(feature_range=(-1.0, 2.0)).fit(X)}
+    for kind, sk in ref.items():
+        want = sk.transform(X)
+        have = np.concatenate([g[3][kind][0] for g in got])
+        np.testing.assert_allclose(have, want, rtol=1e-12, atol=1e-12, equal_nan=True)
+        for g in got:
+            np.testing.assert_allclose(g[3][kind][1], sk.scale_, rtol=1e-12)
+            np.testing.assert_allclose(g[3][kind][2], sk.mean_ if kind == "standard" else sk.min_, rtol=1e-12, atol=1e-12)
