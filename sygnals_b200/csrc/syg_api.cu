@@ -336,6 +336,11 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         for (size_t i = 0; i < slots.size(); ++i) slots[i] = make_int4(ms.desc[4 * i], ms.desc[4 * i + 1], ms.desc[4 * i + 2], ms.desc[4 * i + 3]);
         if ((rc = upload_table(ctx, key + ":ps", slots, &a.mel_slots))) return rc;
         if ((rc = upload_table(ctx, key + ":pw", ms.w, &a.mel_pw))) return rc;
+        {
+            std::string kn = key + ":pwn";                       // float4 count of the tap table (host side cache)
+            if (!ctx->host_ints.count(kn)) ctx->host_ints[kn] = std::vector<int>{(int)(ms.w.size() / 4)};
+            a.mel_pw_f4 = ctx->host_ints[kn][0];
+        }
         a.n_mels = p->n_mels;
         a.mel_power_is_2 = (p->power == 2.0);
         a.mel_half_power = (float)(0.5 * p->power);

@@ -39,6 +39,10 @@ struct WarpTile {
     static constexpr int RS = ((2 * ZS > PS ? 2 * ZS : PS) + 3) / 4 * 4;
     static constexpr int warp_floats = FW * RS;
     static constexpr size_t bytes = (size_t)kWarps * warp_floats * sizeof(float);
+    // plan tables kept in shared memory by the fused kernel (all 16-byte multiples): window [2M] floats, tw [M] float2,
+    // twsh [M/2+1] float2, mel slots [n_mels] int4, mel taps [mel_pw_f4] float4
+    static constexpr int kWinB = 2 * M * 4, kTwB = M * 8, kTwshB = ((M / 2 + 1) * 8 + 15) / 16 * 16;
+    static size_t table_bytes(int n_mels, int mel_pw_f4) { return (size_t)kWinB + kTwB + kTwshB + (size_t)n_mels * 16 + (size_t)mel_pw_f4 * 16; }
 };
 
 template <int LOG2E>
@@ -106,6 +110,32 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     for (int i = lane; i < WF; i += 32) wbase[i] = 0.0f;
     __syncwarp();
 
+    // STAGE 0: the plan tables (window, twiddles, mel taps: ~38 KB for n_fft 2048 / 128 mels) live in shared memory behind the
+    // warps' regions -- 116 table loads per lane and frame become LDS with no L1 tag traffic and no misses
+    constexpr bool TBL = (STAGE == 0);
+    unsigned char* const tb = smem_raw + (size_t)WT::kWarps * WF * sizeof(float);
+    const float2* const t_win = TBL ? reinterpret_cast<const float2*>(tb) : reinterpret_cast<const float2*>(a.window);
+    const float2* const t_tw = TBL ? reinterpret_cast<const float2*>(tb + WT::kWinB) : a.tw;
+    const float2* const t_twsh = TBL ? reinterpret_cast<const float2*>(tb + WT::kWinB + WT::kTwB) : a.twsh;
+    const int4* const t_slots = TBL ? reinterpret_cast<const int4*>(tb + WT::kWinB + WT::kTwB + WT::kTwshB) : a.mel_slots;
+    const float4* const t_melw = TBL ? reinterpret_cast<const float4*>(tb + WT::kWinB + WT::kTwB + WT::kTwshB + (size_t)a.n_mels * 16)
+                                     : reinterpret_cast<const float4*>(a.mel_pw);
+    if (TBL) {
+        float2* d_win = const_cast<float2*>(t_win);
+        for (int i = tid; i < M; i += NT) d_win[i] = __ldg(reinterpret_cast<const float2*>(a.window) + i);
+        float2* d_tw = const_cast<float2*>(t_tw);
+        for (int i = tid; i < M; i += NT) d_tw[i] = __ldg(a.tw + i);
+        float2* d_twsh = const_cast<float2*>(t_twsh);
+        for (int i = tid; i <= M / 2; i += NT) d_twsh[i] = __ldg(a.twsh + i);
+        if (a.mask & syg::FB_MFCC) {
+            int4* d_sl = const_cast<int4*>(t_slots);
+            for (int i = tid; i < a.n_mels; i += NT) d_sl[i] = __ldg(a.mel_slots + i);
+            float4* d_mw = const_cast<float4*>(t_melw);
+            for (int i = tid; i < a.mel_pw_f4; i += NT) d_mw[i] = __ldg(reinterpret_cast<const float4*>(a.mel_pw) + i);
+        }
+        __syncthreads();
+    }
+
     const long long n_tasks = (a.n_frames + FW - 1) / FW;
     const bool small = a.n_frames <= 0x7fffffffLL;                   // 32-bit index arithmetic (a 64-bit division costs ~100 instructions)
     // all warps of the CTA run the same number of iterations (tasks past the end are processed as empty frames)
@@ -130,13 +160,13 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         {
             const float* src = a.y + ur.start + p0;
             const bool interior = (p0 >= 0) && (p0 + 2 * M <= ur.valid) && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
-            const float2* w2 = reinterpret_cast<const float2*>(a.window);
+            const float2* w2 = t_win;
             if (__all_sync(kFull, interior)) {
                 SYG_UNROLL
                 for (int r = 0; r < E; ++r) {
                     const int c = j + r * G;
                     const float2 v = __ldg(reinterpret_cast<const float2*>(src) + c);
-                    const float2 w = __ldg(w2 + c);
+                    const float2 w = TBL ? w2[c] : __ldg(w2 + c);
                     sq2 = __ffma2_rn(v, v, sq2);
                     pk = fmaxf(pk, fabsf(v.x));
                     pk2 = fmaxf(pk2, fabsf(v.y));
@@ -161,7 +191,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     else if (refl) v.x = __ldg(yb + reflect_index(pos, nv));
                     if (pos + 1 >= 0 && pos + 1 < nv) v.y = __ldg(yb + pos + 1);
                     else if (refl) v.y = __ldg(yb + reflect_index(pos + 1, nv));
-                    const float2 w = __ldg(w2 + c);
+                    const float2 w = TBL ? w2[c] : __ldg(w2 + c);
                     sq2 = __ffma2_rn(v, v, sq2);
                     pk = fmaxf(pk, fabsf(v.x));
                     pk2 = fmaxf(pk2, fabsf(v.y));
@@ -197,7 +227,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             constexpr int SH = TL::LOG2M - ilog2(E * R2);             // = 0: W_{E*R2} = W_M
             SYG_UNROLL
             for (int r = 1; r < R2; ++r) {
-                const float2 w = __ldg(&a.tw[(r * k) << SH]);
+                const float2 w = TBL ? t_tw[(r * k) << SH] : __ldg(&t_tw[(r * k) << SH]);
                 cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
             }
             dft_dif_p<R2, 1>(z + q * R2);
@@ -255,7 +285,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     }
                     continue;
                 }
-                const float2 wh = __ldg(&a.twsh[k]);
+                const float2 wh = TBL ? t_twsh[k] : __ldg(&t_twsh[k]);
                 float pwk, pwm;
                 split_power(zk[i], zm[i], wh, pwk, pwm);
                 pk0[kk + ((kk >> 5) << 2)] = pwk;
@@ -468,7 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
 
         // ---------------- mel energies: one filter per lane, 32 filters of similar span per sweep (syg_plan.h) ----------------
         if (a.mask & syg::FB_MFCC) {
-            const float4* const mw4 = reinterpret_cast<const float4*>(a.mel_pw);
+            const float4* const mw4 = t_melw;
             for (int ff = 0; ff < FW; ++ff) {
                 const long long gff = task * FW + ff;
                 if (gff >= a.n_frames) break;
@@ -476,7 +506,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 float fmx = 0.0f;
                 for (int base = 0; base < a.n_mels; base += 32) {
                     const int slot = min(base + lane, a.n_mels - 1);
-                    const int4 d = __ldg(&a.mel_slots[slot]);           // {filter, first padded word, steps, tap offset}: steps/offset are warp uniform
+                    const int4 d = TBL ? t_slots[slot] : __ldg(&t_slots[slot]);           // {filter, first padded word, steps, tap offset}: steps/offset are warp uniform
                     const float4* wv = mw4 + d.w + lane;
                     const float4* pp4 = reinterpret_cast<const float4*>(pfr + d.y);
                     float acc = 0.0f;
@@ -488,7 +518,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                         for (int i = 0; i < d.z; i += 4) {              // steps come in multiples of four (syg_plan.h)
                             SYG_UNROLL
                             for (int c = 0; c < 4; ++c) {
-                                const float4 w = __ldg(wv + 32 * (i + c));
+                                const float4 w = TBL ? wv[32 * (i + c)] : __ldg(wv + 32 * (i + c));
                                 const float4 q = pp4[i + c];
                                 m01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(q.x, q.y), m01);
                                 m23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(q.z, q.w), m23);
@@ -497,7 +527,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                         acc = (m01.x + m01.y) + (m23.x + m23.y);
                     } else {
                         for (int i = 0; i < d.z; ++i) {
-                            const float4 w = __ldg(wv + 32 * i);
+                            const float4 w = TBL ? wv[32 * i] : __ldg(wv + 32 * i);
                             const float4 q = pp4[i];
                             acc = __fmaf_rn(w.x, powf(q.x, a.mel_half_power), acc);
                             acc = __fmaf_rn(w.y, powf(q.y, a.mel_half_power), acc);

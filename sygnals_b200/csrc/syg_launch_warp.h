@@ -13,14 +13,17 @@ template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using WT = sygdev::WarpTile<TL, NT>;
     static int blocks_per_sm[2] = {0, 0};
+    static size_t smem_seen[2] = {0, 0};
     auto kfn = sygdev::frame_warp_kernel<TL, EXTRA, NT, MINB, STAGE>;
     size_t smem = (size_t)WT::kWarps * WT::FW * (STAGE == 2 ? WT::PS : WT::RS) * sizeof(float);
     const int wide = (STAGE == 3 && a.out_kind == 0) ? 1 : 0;        // complex64 tile
+    if (STAGE == 0) smem += WT::table_bytes(a.n_mels, (a.mask & syg::FB_MFCC) ? a.mel_pw_f4 : 0);
     if (STAGE == 3) {
         const int TT = WT::kWarps * WT::FW;
         smem += (size_t)TT * sizeof(long long) + (size_t)(WT::M + 1) * (TT + 1) * (wide ? 8 : 4);
     }
-    if (blocks_per_sm[wide] == 0) {
+    if (blocks_per_sm[wide] == 0 || smem > smem_seen[wide]) {
+        smem_seen[wide] = smem;
         LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + (STAGE == 3 && !wide ? (WT::M + 1) * (WT::kWarps * WT::FW + 1) * 4 : 0)));
         int nb = 0;
         LCK(SYG_OCCUPANCY(nb, kfn, NT, smem));
@@ -47,7 +50,10 @@ static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count,
         case 7: return frame_warp_t<FftTile<7, 16>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
         case 8: return frame_warp_t<FftTile<8, 16>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
         case 9: return frame_warp_t<FftTile<9, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
-        case 10: return frame_warp_t<FftTile<10, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+        case 10:
+            // fused: one CTA of 16 warps per SM so that the 38 KB of plan tables are held once (leaves ~50 KB of L1)
+            if (STAGE == 0) return frame_warp_t<FftTile<10, 32>, EXTRA, 512, 1, STAGE>(a, sm_count, st, err);
+            return frame_warp_t<FftTile<10, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
     }
     err = "n_fft=" + std::to_string(n_fft) + " has no warp tile";
     return -5;
