@@ -178,7 +178,7 @@ int launch_features(int n_fft, int stage, const syg::FrameArgs& a, int sm_count,
 }
 
 // words per spectrum of the warp kernel (= WarpTile::PS) and frames per warp task (= WarpTile::FW)
-int warp_ps_words(int n_fft) { const int nb = n_fft / 2 + 1; return ((nb + 4 * (nb >> 5) + 16 + 3) / 4) * 4; }
+int warp_ps_words(int n_fft) { const int nb = n_fft / 2 + 1; return ((nb + 4 * (nb >> 5) + 48 + 3) / 4) * 4; }
 int warp_fw(int n_fft) {
     switch (ilog2i(n_fft / 2)) { case 4: return 8; case 5: return 8; case 6: return 4; case 7: return 4; case 8: return 2; case 9: return 2; default: return 1; }
 }

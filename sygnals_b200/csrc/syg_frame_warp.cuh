@@ -32,7 +32,7 @@ struct WarpTile {
     static constexpr int FW = 32 / G;                         // frames per warp
     static constexpr int R2 = TL::RLAST;                      // radix of pass 2
     static constexpr int ZS = M + (M >> LOG2E) + 1;           // float2 slots per frame
-    static constexpr int PS = ((M + 1) + 4 * ((M + 1) >> 5) + 16 + 3) / 4 * 4;  // floats per frame: 4 pad words per 32 bins (ppad) + 16 words of sweep slack
+    static constexpr int PS = ((M + 1) + 4 * ((M + 1) >> 5) + 48 + 3) / 4 * 4;  // floats per frame: 4 pad words per 32 bins (ppad) + 48 words of sweep slack
     static constexpr int kWarps = NT / 32;
     // one region per frame, used twice: as the Z exchange buffer of the FFT, then (Z is dead once the real split has pulled
     // its pairs into registers) as the |X|^2 spectrum.  Halves the shared memory per warp, which the SM hands to L1.
@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         float2* d_win = const_cast<float2*>(t_win);
         for (int i = tid; i < M; i += NT) d_win[i] = __ldg(reinterpret_cast<const float2*>(a.window) + i);
         float2* d_tw = const_cast<float2*>(t_tw);
-        for (int i = tid; i < M; i += NT) d_tw[i] = __ldg(a.tw + i);
+        // transposed for the pass-2 access: entry [r][k] = W_M^{r k} (r < R2, k < E; R2 E = M), so that the lanes of a warp
+        // (consecutive k) read consecutive words instead of stride-r ones
+        for (int i = tid; i < M; i += NT) d_tw[i] = __ldg(a.tw + (i / E) * (i % E));
         float2* d_twsh = const_cast<float2*>(t_twsh);
         for (int i = tid; i <= M / 2; i += NT) d_twsh[i] = __ldg(a.twsh + i);
         if (a.mask & syg::FB_MFCC) {
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             constexpr int SH = TL::LOG2M - ilog2(E * R2);             // = 0: W_{E*R2} = W_M
             SYG_UNROLL
             for (int r = 1; r < R2; ++r) {
-                const float2 w = TBL ? t_tw[(r * k) << SH] : __ldg(&t_tw[(r * k) << SH]);
+                const float2 w = TBL ? t_tw[r * E + k] : __ldg(&t_tw[(r * k) << SH]);
                 cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
             }
             dft_dif_p<R2, 1>(z + q * R2);

@@ -134,7 +134,7 @@ inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
     // the group's taps are interleaved [step][lane] so one LDG.128 per step is a fully coalesced 512-byte read.
     //   desc[slot] = {filter, first padded word (multiple of 4), L, offset of the group's taps in float4 units}
     auto ppad = [](int k) { return k + ((k >> 5) << 2); };
-    const int ps_words = ((n_bins + 4 * (n_bins >> 5) + 16 + 3) / 4) * 4;     // = WarpTile::PS
+    const int ps_words = ((n_bins + 4 * (n_bins >> 5) + 48 + 3) / 4) * 4;     // = WarpTile::PS
     std::vector<int> order(t.n_mels);
     for (int i = 0; i < t.n_mels; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return t.len[a] > t.len[b]; });
@@ -143,15 +143,52 @@ inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
     for (int g0 = 0; g0 < t.n_mels; g0 += 32) {
         const int gn = std::min(32, t.n_mels - g0);
         int L = 1;
-        std::vector<int> pst(gn, 0);
+        std::vector<int> pst(gn, 0), len(gn, 1);
         for (int j = 0; j < gn; ++j) {
             const int m = order[g0 + j];
             if (t.len[m] <= 0) continue;
             pst[j] = ppad(t.start[m]) & ~3;
-            L = std::max(L, (ppad(t.start[m] + t.len[m] - 1) - pst[j] + 1 + 3) / 4);
+            len[j] = (ppad(t.start[m] + t.len[m] - 1) - pst[j] + 1 + 3) / 4;
+            L = std::max(L, len[j]);
+        }
+        // Bank conflicts: the 8 lanes of a quarter warp read one float4 each per step; they are conflict free when their
+        // first float4 indices differ mod 8 (all lanes advance together).  A slot may start up to 7 float4 earlier (zero
+        // weights in front), which costs steps only if it pushes the slot beyond the group's longest; per quarter the
+        // assignment of residues that minimises that overshoot is found by exhaustive search (8! orders, plan time only).
+        for (int q0 = 0; q0 < gn; q0 += 8) {
+            const int qn = std::min(8, gn - q0);
+            int perm[8] = {0, 1, 2, 3, 4, 5, 6, 7}, best[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            long best_cost = -1;
+            do {
+                long cost = 0;
+                int over = 0;
+                for (int j = 0; j < qn; ++j) {
+                    const int res = (pst[q0 + j] / 4) & 7;
+                    int d = (res - perm[j]) & 7;                          // float4 steps to move the start down
+                    if (pst[q0 + j] - 4 * d < 0) d = 0;                    // cannot start before the spectrum: keep (may conflict)
+                    over = std::max(over, len[q0 + j] + d);
+                    cost += d;
+                }
+                const long c = (long)std::max(over, L) * 1000 + cost;      // first the group length, then the total padding
+                if (best_cost < 0 || c < best_cost) { best_cost = c; for (int j = 0; j < 8; ++j) best[j] = perm[j]; }
+            } while (std::next_permutation(perm, perm + 8));
+            for (int j = 0; j < qn; ++j) {
+                const int res = (pst[q0 + j] / 4) & 7;
+                int d = (res - best[j]) & 7;
+                if (pst[q0 + j] - 4 * d < 0) d = 0;
+                pst[q0 + j] -= 4 * d;
+                len[q0 + j] += d;
+                L = std::max(L, len[q0 + j]);
+            }
         }
         L = (L + 3) / 4 * 4;                                      // the kernel sweeps four steps per iteration
-        for (int j = 0; j < gn; ++j) pst[j] = std::max(0, std::min(pst[j], ps_words - 4 * L));   // keep the sweep inside the buffer
+        for (int j = 0; j < gn; ++j) {                              // keep the sweep inside the buffer, and the bank residue with it
+            const int limit = ps_words - 4 * L;
+            if (pst[j] > limit) {
+                const int keep = limit - 4 * (((limit / 4) - (pst[j] / 4)) & 7);
+                pst[j] = keep >= 0 ? keep : std::max(0, limit);
+            }
+        }
         const int goff4 = (int)(s.w.size() / 4);
         s.w.resize(s.w.size() + (size_t)L * 32 * 4, 0.0f);
         for (int j = 0; j < gn; ++j) {
