@@ -1,6 +1,9 @@
 // Welch / periodogram kernel instantiations
+#include <cstdlib>
+
 #include "syg_launch_common.h"
 #include "syg_kernels.cuh"
+#include "syg_welch_warp.cuh"
 
 namespace syglaunch {
 
@@ -23,8 +26,42 @@ static int welch_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::
     return 0;
 }
 
+template <class TL>
+static int welch_warp_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err) {
+    constexpr int NT = 256;
+    using WW = sygdev::WelchWarpTile<TL, NT>;
+    static int blocks_per_sm = 0;
+    auto kfn = sygdev::welch_warp_kernel<TL, NT, 2>;
+    if (blocks_per_sm == 0) {
+        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WW::bytes));
+        int nb = 0;
+        LCK(SYG_OCCUPANCY(nb, kfn, NT, WW::bytes));
+        if (nb < 1) { err = "welch_warp kernel does not fit on an SM"; return -3; }
+        blocks_per_sm = nb;
+    }
+    if (a.g.n_units <= 0) return 0;
+    const long long want = (a.g.n_units + NT / 32 - 1) / (NT / 32);
+    const int grid = (int)std::min<long long>(want, (long long)sm_count * blocks_per_sm);
+    SYG_LAUNCH(kfn, grid, NT, WW::bytes, st, a);
+    LCK(cudaGetLastError());
+    return 0;
+}
+
 int welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using namespace sygdev;
+    static int env = -1;                                                // SYGB200_WELCH_BLOCK=1: the CTA-cooperative kernel for every nfft
+    if (env < 0) { const char* e = std::getenv("SYGB200_WELCH_BLOCK"); env = e ? std::atoi(e) : 0; }
+    if (!env && nfft <= 2048) {
+        switch (ilog2i(nfft / 2)) {
+            case 4: return welch_warp_t<FftTile<4, 4>>(a, sm_count, st, err);
+            case 5: return welch_warp_t<FftTile<5, 8>>(a, sm_count, st, err);
+            case 6: return welch_warp_t<FftTile<6, 8>>(a, sm_count, st, err);
+            case 7: return welch_warp_t<FftTile<7, 16>>(a, sm_count, st, err);
+            case 8: return welch_warp_t<FftTile<8, 16>>(a, sm_count, st, err);
+            case 9: return welch_warp_t<FftTile<9, 32>>(a, sm_count, st, err);
+            case 10: return welch_warp_t<FftTile<10, 32>>(a, sm_count, st, err);
+        }
+    }
     switch (ilog2i(nfft / 2)) {
         case 4: return welch_t<FftTile<4, 4>>(a, sm_count, st, err);
         case 5: return welch_t<FftTile<5, 8>>(a, sm_count, st, err);

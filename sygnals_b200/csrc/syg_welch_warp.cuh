@@ -1,0 +1,208 @@
+// sygnals_b200/csrc/syg_welch_warp.cuh
+//
+// welch_warp_kernel<TL>: Welch / periodogram PSD for nfft <= 2048, warp-synchronous like the feature kernel.
+//
+// One WARP owns one unit (e.g. one channel-second): it walks the unit's sub-segments FW at a time (FW = 32 / G frames per
+// warp), per sub-segment: detrend('constant') -> window -> packed real FFT in registers (FP32x2 butterflies) -> |X|^2 added to
+// the warp's private accumulator in shared memory.  After the last sub-segment the FW accumulators are summed in a fixed
+// order, scaled (1 / (fs sum w^2) or 1 / (sum w)^2, one-sided doubling except DC / Nyquist) and stored; the unit's rms / crest /
+// peak come from one more streaming pass over its samples.  No CTA barrier, no atomics, deterministic.
+//
+// Reference semantics: scipy.signal.welch / periodogram behind sygnals/core/dsp.py:495-560, :434-493; crest_factor of
+// sygnals/core/features/time_domain.py:149-184 applied to the unit.
+#pragma once
+
+#include "syg_frame_warp.cuh"
+
+namespace sygdev {
+
+template <class TL, int NT>
+struct WelchWarpTile {
+    using WT = WarpTile<TL, NT>;
+    static constexpr int FW = WT::FW, ZS = WT::ZS, PS = WT::PS;
+    static constexpr int ZR = (2 * ZS + 3) / 4 * 4;                  // floats of one Z region
+    static constexpr int warp_floats = FW * (ZR + PS);               // Z regions, then the accumulators
+    static constexpr size_t bytes = (size_t)WT::kWarps * warp_floats * sizeof(float);
+};
+
+template <class TL, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchArgs a) {
+    using WT = WarpTile<TL, NT>;
+    using WW = WelchWarpTile<TL, NT>;
+    constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, PS = WT::PS, LE = WT::LOG2E;
+    constexpr int Q = E / R2;
+    constexpr int B = M + 1;
+    SYG_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int f = lane / G, j = lane % G;
+    float* const wbase = reinterpret_cast<float*>(smem_raw) + warp * WW::warp_floats;
+    float2* const zs = reinterpret_cast<float2*>(wbase + f * WW::ZR);
+    float* const accw = wbase + FW * WW::ZR;                          // [FW][PS], ppad layout
+    float* const acc = accw + f * PS;
+    const float2* const w2 = reinterpret_cast<const float2*>(a.window);
+    const bool full = (a.nperseg == 2 * M);
+    const float inv_n = 1.0f / (float)a.nperseg;
+
+    const long long warps = (long long)gridDim.x * WT::kWarps;
+    for (long long u = (long long)blockIdx.x * WT::kWarps + warp; u < a.g.n_units; u += warps) {
+        const UnitRef ur = unit_ref(a.g, u);
+        const float* yb = a.y + ur.start;
+        for (int i = lane; i < FW * PS; i += 32) accw[i] = 0.0f;
+        __syncwarp();
+        for (int s0 = 0; s0 < a.nseg; s0 += FW) {
+            const int s = s0 + f;
+            const bool valid = s < a.nseg;
+            const long long p0 = (long long)s * a.step;
+            const long long nv = valid ? ur.valid : 0;
+            // ---------------- load, detrend, window ----------------
+            float2 z[E];
+            const float* src = yb + p0;
+            const bool interior = full && valid && (p0 + 2 * M <= nv) && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
+            float2 sm01 = make_float2(0.0f, 0.0f), sm23 = sm01;
+            if (__all_sync(kFull, interior)) {
+                SYG_UNROLL
+                for (int r = 0; r < E; ++r) {
+                    z[r] = __ldg(reinterpret_cast<const float2*>(src) + j + r * G);
+                    if (r & 1) sm23 = __fadd2_rn(sm23, z[r]); else sm01 = __fadd2_rn(sm01, z[r]);
+                }
+            } else {
+                SYG_UNROLL
+                for (int r = 0; r < E; ++r) {
+                    const int c = j + r * G;
+                    const long long pos = p0 + 2 * c;
+                    float2 v = make_float2(0.0f, 0.0f);
+                    if (2 * c < a.nperseg && pos < nv) v.x = __ldg(yb + pos);
+                    if (2 * c + 1 < a.nperseg && pos + 1 < nv) v.y = __ldg(yb + pos + 1);
+                    z[r] = v;
+                    if (r & 1) sm23 = __fadd2_rn(sm23, v); else sm01 = __fadd2_rn(sm01, v);
+                }
+            }
+            float mean = 0.0f;
+            if (a.detrend) {                                          // scipy detrend('constant'): subtract the sub-segment mean
+                const double tot = lanes_sum<G>((double)((sm01.x + sm01.y) + (sm23.x + sm23.y)));
+                mean = (float)(tot * (double)inv_n);
+            }
+            SYG_UNROLL
+            for (int r = 0; r < E; ++r) {
+                const float2 w = __ldg(w2 + j + r * G);               // zero beyond nperseg: padding samples vanish
+                z[r] = make_float2((z[r].x - mean) * w.x, (z[r].y - mean) * w.y);
+            }
+            // ---------------- FFT (as in frame_warp_kernel) ----------------
+            dft_dif_p<E, 1>(z);
+            SYG_UNROLL
+            for (int kp = 0; kp < E; ++kp) zs[zpad<LE>(j * E + kp)] = z[bitrev(kp, LE)];
+            __syncwarp();
+            SYG_UNROLL
+            for (int q = 0; q < Q; ++q) {
+                const int b = j + q * G;
+                SYG_UNROLL
+                for (int r = 0; r < R2; ++r) z[q * R2 + r] = zs[zpad<LE>(b + r * (M / R2))];
+            }
+            __syncwarp();
+            SYG_UNROLL
+            for (int q = 0; q < Q; ++q) {
+                const int b = j + q * G;
+                const int k = b & (E - 1);
+                SYG_UNROLL
+                for (int r = 1; r < R2; ++r) {
+                    const float2 w = __ldg(&a.tw[r * k]);
+                    cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
+                }
+                dft_dif_p<R2, 1>(z + q * R2);
+                const int ob = (b - k) * R2 + k;
+                SYG_UNROLL
+                for (int kp = 0; kp < R2; ++kp) zs[zpad<LE>(ob + kp * E)] = z[q * R2 + bitrev(kp, ilog2(R2))];
+            }
+            __syncwarp();
+            // ---------------- real split -> accumulate |X[k]|^2 ----------------
+            {
+                const int jz = (j == 0) ? 1 : 0;
+                const float2* const zk0 = zs + j;
+                const float2* const zm0 = zs - j;
+                const float2* const zm1 = zm0 + jz;
+                float* const pk0 = acc + j;
+                float* const pm0 = acc - j;
+                float* const pm1 = pm0 + 4 * jz;
+                SYG_UNROLL
+                for (int i = 0; i <= E / 2; ++i) {
+                    const int kk = i * G;
+                    const int k = j + kk;
+                    if (i == E / 2 && j != 0) break;
+                    const float2 zk = zk0[kk + (kk >> LE)];
+                    const int c1 = (M - kk) + ((M - kk - 1) >> LE);
+                    const bool blk = ((M - kk) & (E - 1)) == 0;
+                    float2 zm = blk ? zm1[c1] : zm0[c1];
+                    if (i == 0 && j == 0) zm = zk;
+                    const float2 w = __ldg(&a.tws[k]);
+                    float xkr, xki, xmr, xmi;
+                    real_split(zk.x, zk.y, zm.x, zm.y, w.x, w.y, xkr, xki, xmr, xmi);
+                    if (valid) {
+                        pk0[kk + ((kk >> 5) << 2)] += __fmaf_rn(xkr, xkr, xki * xki);
+                        const int q1 = (M - kk) + (((M - kk - 1) >> 5) << 2);
+                        const bool blk5 = ((M - kk) & 31) == 0;
+                        if (2 * k != M) (blk5 ? pm1 : pm0)[q1] += __fmaf_rn(xmr, xmr, xmi * xmi);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---------------- mean over sub-segments (fixed order), scaling, store ----------------
+        const float inv = a.scale / (float)a.nseg;
+        for (int k = lane; k < B; k += 32) {
+            float v = 0.0f;
+            SYG_UNROLL
+            for (int ff = 0; ff < FW; ++ff) v += accw[ff * PS + ppad(k)];
+            v *= inv;
+            if (a.onesided_double && k != 0 && k != M) v *= 2.0f;
+            a.psd[u * B + k] = v;
+        }
+        if (a.stats) {                                                // rms / crest / peak of the whole unit
+            float2 sq = make_float2(0.0f, 0.0f);
+            double sqd = 0.0;
+            float pk = 0.0f;
+            long long i = 0;
+            if (ur.valid >= a.g.unit_len && (reinterpret_cast<uintptr_t>(yb) & 15u) == 0) {       // whole unit present, 16-byte aligned
+                const float4* y4 = reinterpret_cast<const float4*>(yb);
+                const long long n4 = a.g.unit_len >> 2;
+                int run = 0;
+                float2 sq2 = make_float2(0.0f, 0.0f);
+                for (long long q = lane; q < n4; q += 32) {
+                    const float4 v = __ldg(y4 + q);
+                    sq = __ffma2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y), sq);
+                    sq2 = __ffma2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w), sq2);
+                    pk = fmaxf(pk, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                    if (++run == 16) {                                 // float32 partial sums of 64 terms, float64 across
+                        sqd += (double)((sq.x + sq.y) + (sq2.x + sq2.y));
+                        sq = make_float2(0.0f, 0.0f); sq2 = sq; run = 0;
+                    }
+                }
+                sqd += (double)((sq.x + sq.y) + (sq2.x + sq2.y));
+                sq = make_float2(0.0f, 0.0f);
+                i = n4 << 2;
+            }
+            int run = 0;
+            for (i += lane; i < a.g.unit_len; i += 32) {
+                const float v = (i < ur.valid) ? __ldg(yb + i) : 0.0f;
+                sq.x = __fmaf_rn(v, v, sq.x);
+                pk = fmaxf(pk, fabsf(v));
+                if (++run == 64) { sqd += (double)sq.x; sq.x = 0.0f; run = 0; }
+            }
+            sqd += (double)sq.x;
+            SYG_UNROLL
+            for (int o = 16; o >= 1; o >>= 1) {
+                sqd += __shfl_xor_sync(kFull, sqd, o);
+                pk = fmaxf(pk, __shfl_xor_sync(kFull, pk, o));
+            }
+            if (lane == 0) {
+                const double rms = a.g.unit_len > 0 ? sqrt(sqd / (double)a.g.unit_len) : 0.0;
+                a.stats[u * 3 + 0] = (float)rms;
+                a.stats[u * 3 + 1] = (rms < kEps64) ? 0.0f : (float)((double)pk / rms);
+                a.stats[u * 3 + 2] = pk;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace sygdev
