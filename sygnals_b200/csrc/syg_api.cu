@@ -331,7 +331,7 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         if ((rc = upload_table(ctx, key + ":o", mt.off, &a.mel_off))) return rc;
         if ((rc = upload_table(ctx, key + ":w", mt.w, &a.mel_w))) return rc;
         sygplan::MelSlots ms;
-        if (!ctx->tables.count(key + ":pw")) sygplan::build_mel_slots(mt, ms, fl / 2 + 1);
+        if (!ctx->tables.count(key + ":pw")) sygplan::build_mel_slots(mt, ms, fl / 2 + 1, fl <= 2048 ? 32 / warp_fw(fl) : 32);
         std::vector<int4> slots(ms.desc.size() / 4);
         for (size_t i = 0; i < slots.size(); ++i) slots[i] = make_int4(ms.desc[4 * i], ms.desc[4 * i + 1], ms.desc[4 * i + 2], ms.desc[4 * i + 3]);
         if ((rc = upload_table(ctx, key + ":ps", slots, &a.mel_slots))) return rc;
@@ -439,19 +439,15 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
         f.cws = a.cws;
         f.unit_max = a.unit_max;
         f.out = out;
-        const int gx = (pl.T + sygdev::kFinTT - 1) / sygdev::kFinTT;
         const size_t smem = (size_t)sygdev::kFinTT * (f.n_mels + 3) * sizeof(double);   // two folded halves (or one full tile) + padding
-        for (long long u0 = 0; u0 < g.n_units; u0 += 65535) {       // gridDim.y limit
-            syg::FinalizeArgs fc = f;
-            fc.n_units = std::min<long long>(65535, g.n_units - u0);
-            fc.melws = f.melws + (size_t)u0 * pl.T * f.n_mels;
-            fc.cws = f.cws + (size_t)u0 * pl.T * 2 * f.nb;
-            fc.unit_max = f.unit_max + u0 * 4;
-            fc.out = out + (size_t)u0 * pl.n_rows * pl.T;
-            std::string err;
-            const int frc = syglaunch::finalize(fc, (unsigned)gx, (unsigned)fc.n_units, smem, st, err);
-            if (frc) return fail(frc, "%s", err.c_str());
-        }
+        const long long n_tiles = (g.n_units * (long long)pl.T + sygdev::kFinTT - 1) / sygdev::kFinTT;
+        static int fin_cap = -1;                                      // SYGB200_FIN_CTAS: CTAs per SM of the finalize grid (0 = one CTA per tile)
+        if (fin_cap < 0) { const char* e = std::getenv("SYGB200_FIN_CTAS"); fin_cap = e ? std::atoi(e) : 0; }
+        const long long cap = fin_cap > 0 ? (long long)ctx->sm_count * fin_cap : 0x7fffffffLL;
+        const unsigned grid = (unsigned)std::min<long long>(n_tiles, cap);
+        std::string err;
+        const int frc = syglaunch::finalize(f, grid, 1u, smem, st, err);
+        if (frc) return fail(frc, "%s", err.c_str());
     }
     return SYG_OK;
 }

@@ -498,54 +498,54 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             }
         }
 
-        // ---------------- mel energies: one filter per lane, 32 filters of similar span per sweep (syg_plan.h) ----------------
+        // ---------------- mel energies: one filter per lane; the warp sweeps GS = 32 / FW filters of each of its frames at once ----------------
         if (a.mask & syg::FB_MFCC) {
+            constexpr int GS = 32 / FW;
+            const int mf = lane / GS, sl = lane % GS;                   // frame of the warp task, slot within the sweep group
+            const long long gmf = task * FW + mf;
+            const bool fvalid = gmf < a.n_frames;
+            const float* pfr = pww + mf * RSS;
             const float4* const mw4 = t_melw;
-            for (int ff = 0; ff < FW; ++ff) {
-                const long long gff = task * FW + ff;
-                if (gff >= a.n_frames) break;
-                const float* pfr = pww + ff * RSS;
-                float fmx = 0.0f;
-                for (int base = 0; base < a.n_mels; base += 32) {
-                    const int slot = min(base + lane, a.n_mels - 1);
-                    const int4 d = TBL ? t_slots[slot] : __ldg(&t_slots[slot]);           // {filter, first padded word, steps, tap offset}: steps/offset are warp uniform
-                    const float4* wv = mw4 + d.w + lane;
-                    const float4* pp4 = reinterpret_cast<const float4*>(pfr + d.y);
-                    float acc = 0.0f;
-                    if (a.mel_power_is_2) {
-                        float2 m01 = make_float2(0.0f, 0.0f), m23 = m01;
+            float fmx = 0.0f;
+            for (int base = 0; base < a.n_mels; base += GS) {
+                const int slot = min(base + sl, a.n_mels - 1);
+                const int4 d = TBL ? t_slots[slot] : __ldg(&t_slots[slot]);   // {filter, first padded word, steps, tap offset}: steps/offset are warp uniform
+                const float4* wv = mw4 + d.w + sl;
+                const float4* pp4 = reinterpret_cast<const float4*>(pfr + d.y);
+                float acc = 0.0f;
+                if (a.mel_power_is_2) {
+                    float2 m01 = make_float2(0.0f, 0.0f), m23 = m01;
 #ifndef SYG_EMU
 #pragma unroll 1
 #endif
-                        for (int i = 0; i < d.z; i += 4) {              // steps come in multiples of four (syg_plan.h)
-                            SYG_UNROLL
-                            for (int c = 0; c < 4; ++c) {
-                                const float4 w = TBL ? wv[32 * (i + c)] : __ldg(wv + 32 * (i + c));
-                                const float4 q = pp4[i + c];
-                                m01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(q.x, q.y), m01);
-                                m23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(q.z, q.w), m23);
-                            }
-                        }
-                        acc = (m01.x + m01.y) + (m23.x + m23.y);
-                    } else {
-                        for (int i = 0; i < d.z; ++i) {
-                            const float4 w = TBL ? wv[32 * i] : __ldg(wv + 32 * i);
-                            const float4 q = pp4[i];
-                            acc = __fmaf_rn(w.x, powf(q.x, a.mel_half_power), acc);
-                            acc = __fmaf_rn(w.y, powf(q.y, a.mel_half_power), acc);
-                            acc = __fmaf_rn(w.z, powf(q.z, a.mel_half_power), acc);
-                            acc = __fmaf_rn(w.w, powf(q.w, a.mel_half_power), acc);
+                    for (int i = 0; i < d.z; i += 4) {                  // steps come in multiples of four (syg_plan.h)
+                        SYG_UNROLL
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 w = TBL ? wv[GS * (i + c)] : __ldg(wv + GS * (i + c));
+                            const float4 q = pp4[i + c];
+                            m01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(q.x, q.y), m01);
+                            m23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(q.z, q.w), m23);
                         }
                     }
-                    if (base + lane < a.n_mels) {
-                        a.melws[gff * a.n_mels + d.x] = acc;
-                        fmx = fmaxf(fmx, acc);
+                    acc = (m01.x + m01.y) + (m23.x + m23.y);
+                } else {
+                    for (int i = 0; i < d.z; ++i) {
+                        const float4 w = TBL ? wv[GS * i] : __ldg(wv + GS * i);
+                        const float4 q = pp4[i];
+                        acc = __fmaf_rn(w.x, powf(q.x, a.mel_half_power), acc);
+                        acc = __fmaf_rn(w.y, powf(q.y, a.mel_half_power), acc);
+                        acc = __fmaf_rn(w.z, powf(q.z, a.mel_half_power), acc);
+                        acc = __fmaf_rn(w.w, powf(q.w, a.mel_half_power), acc);
                     }
                 }
-                const unsigned mx = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fmx, 0.0f)));
-                const long long uff = __shfl_sync(kFull, u, ff * G);    // unit of frame ff (all lanes take part)
-                if (lane == 0 && mx != 0u) atomicMax(&a.unit_max[uff * 4 + 0], mx);
+                if (base + sl < a.n_mels && fvalid) {
+                    a.melws[gmf * a.n_mels + d.x] = acc;
+                    fmx = fmaxf(fmx, acc);
+                }
             }
+            const float gmx = lanes_max<GS>(fmaxf(fmx, 0.0f));
+            const long long umf = __shfl_sync(kFull, u, mf * G);       // unit of frame mf (all lanes take part)
+            if (sl == 0 && fvalid && gmx > 0.0f) atomicMax(&a.unit_max[umf * 4 + 0], __float_as_uint(gmx));
         }
 
         // ---------------- spectral contrast: per band mean of the n largest / n smallest magnitudes ----------------

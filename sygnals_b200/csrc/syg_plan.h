@@ -127,11 +127,12 @@ inline bool build_mel(double sr, int n_fft, int n_mels, double fmin, double fmax
 // weight at every pad position) and padded to a multiple of 4 taps.  desc = {filter m, padded start, taps, offset}.
 struct MelSlots { std::vector<int> desc; std::vector<float> w; };
 
-inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
+inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins, int gs) {
     // Slots live in the warp kernel's padded spectrum space: ppad(k) = k + 4 * (k / 32) (4 pad words after every 32 bins).
-    // Filters are sorted by span and taken 32 at a time (one per lane); every slot of a group spans the same number L of
-    // float4 steps (the group's longest filter, zero weights elsewhere) so the sweep has a warp-uniform trip count, and
-    // the group's taps are interleaved [step][lane] so one LDG.128 per step is a fully coalesced 512-byte read.
+    // Filters are sorted by span and taken gs at a time (gs = 32 / frames-per-warp: the warp sweeps gs filters of each of
+    // its frames at once); every slot of a group spans the same number L of float4 steps (the group's longest filter, zero
+    // weights elsewhere) so the sweep has a warp-uniform trip count, and the group's taps are interleaved [step][slot] so
+    // one 128-bit read per step is contiguous across the lanes.
     //   desc[slot] = {filter, first padded word (multiple of 4), L, offset of the group's taps in float4 units}
     auto ppad = [](int k) { return k + ((k >> 5) << 2); };
     const int ps_words = ((n_bins + 4 * (n_bins >> 5) + 48 + 3) / 4) * 4;     // = WarpTile::PS
@@ -140,8 +141,8 @@ inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return t.len[a] > t.len[b]; });
     s.desc.assign((size_t)t.n_mels * 4, 0);
     s.w.clear();
-    for (int g0 = 0; g0 < t.n_mels; g0 += 32) {
-        const int gn = std::min(32, t.n_mels - g0);
+    for (int g0 = 0; g0 < t.n_mels; g0 += gs) {
+        const int gn = std::min(gs, t.n_mels - g0);
         int L = 1;
         std::vector<int> pst(gn, 0), len(gn, 1);
         for (int j = 0; j < gn; ++j) {
@@ -190,14 +191,14 @@ inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins) {
             }
         }
         const int goff4 = (int)(s.w.size() / 4);
-        s.w.resize(s.w.size() + (size_t)L * 32 * 4, 0.0f);
+        s.w.resize(s.w.size() + (size_t)L * gs * 4, 0.0f);
         for (int j = 0; j < gn; ++j) {
             const int m = order[g0 + j];
             for (int i = 0; i < 4 * L; ++i) {
                 const int p = pst[j] + i, blk = p / 36, r = p % 36, k = 32 * blk + r;
                 float wv = 0.0f;
                 if (t.len[m] > 0 && r < 32 && k >= t.start[m] && k < t.start[m] + t.len[m]) wv = t.w[t.off[m] + (k - t.start[m])];
-                s.w[((size_t)goff4 + (size_t)(i / 4) * 32 + j) * 4 + (i % 4)] = wv;
+                s.w[((size_t)goff4 + (size_t)(i / 4) * gs + j) * 4 + (i % 4)] = wv;
             }
             int* d = &s.desc[(size_t)(g0 + j) * 4];
             d[0] = m; d[1] = pst[j]; d[2] = L; d[3] = goff4;
