@@ -173,6 +173,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO in the box environment) off it
+        os.environ["NCCL_DEBUG"] = os.environ.get("SYGB200_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
     sr, fl, hop = w["sr"], w["fl"], w["hop"]
