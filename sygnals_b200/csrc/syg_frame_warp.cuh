@@ -81,10 +81,6 @@ SYG_DEVICE SYG_INLINE double lanes_scan_incl(double v, int gl) {
 // that the host sizes to stay in L2; stage 2 (epilogues, 64 registers, 32 warps/SM) stages it into shared memory.  The
 // epilogues are latency bound (serial REDUX pops, min/max networks, dependent loads): twice the resident warps hide what the
 // fused kernel's 4 warps per scheduler cannot.  (CTA barriers between phases were measured and rejected: +8 %.)
-SYG_DEVICE SYG_INLINE long long unit_of(long long frame, int T, bool small) {
-    return small ? (long long)((unsigned)frame / (unsigned)T) : frame / T;
-}
-
 template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameArgs a) {
     using WT = WarpTile<TL, NT>;
@@ -139,14 +135,25 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     }
 
     const long long n_tasks = (a.n_frames + FW - 1) / FW;
-    const bool small = a.n_frames <= 0x7fffffffLL;                   // 32-bit index arithmetic (a 64-bit division costs ~100 instructions)
+    // (unit, frame-in-unit) of this lane's frame advance incrementally: one division per kernel instead of one per frame
+    const long long stride_tasks = (long long)gridDim.x * WT::kWarps;
+    const long long stride_frames = stride_tasks * FW;
+    const long long du = stride_frames / a.T;
+    const int dt = (int)(stride_frames - du * a.T);
+    long long gf_run = ((long long)blockIdx.x * WT::kWarps + warp) * FW + f;
+    long long u_run = gf_run / a.T;
+    int t_run = (int)(gf_run - u_run * a.T);
     // all warps of the CTA run the same number of iterations (tasks past the end are processed as empty frames)
-    for (long long task0 = (long long)blockIdx.x * WT::kWarps; task0 < n_tasks; task0 += (long long)gridDim.x * WT::kWarps) {
+    for (long long task0 = (long long)blockIdx.x * WT::kWarps; task0 < n_tasks; task0 += stride_tasks) {
         const long long task = task0 + warp;
-        const long long gf = task * FW + f;
+        const long long gf = gf_run;
         const bool valid = gf < a.n_frames;
-        const long long u = valid ? unit_of(gf, a.T, small) : 0;
-        const int t = valid ? (int)(gf - u * a.T) : 0;
+        const long long u = valid ? u_run : 0;
+        const int t = valid ? t_run : 0;
+        gf_run += stride_frames;
+        u_run += du;
+        t_run += dt;
+        if (t_run >= a.T) { t_run -= a.T; ++u_run; }
         UnitRef ur = unit_ref(a.g, u);
         if (!valid) ur.valid = 0;
         const long long p0 = (long long)t * a.hop - a.cpad;
