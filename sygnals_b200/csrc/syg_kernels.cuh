@@ -344,6 +344,105 @@ __global__ void __launch_bounds__(kThreads) frame_kernel(const syg::FrameArgs a)
 }
 
 // --------------------------------------------------------------------------------------------------------
+// stft_tile_kernel<TL, TT>: STFT output for the large transforms (n_fft 4096 / 8192; the warp kernel covers the rest).
+// A CTA owns TT consecutive frames at a time: its F = kThreads / G frame groups run TT / F rounds of the CTA-cooperative FFT,
+// every round drops X / |X| / |X|^2 into a transposed shared-memory tile [B][TT + 1], then the tile leaves as rows of TT
+// consecutive frames per bin -- the reference layout is (1 + n_fft/2, T) with frames innermost (dsp.py:167-229), so per-frame
+// stores would touch one 32-byte sector for every 4-byte value.
+// --------------------------------------------------------------------------------------------------------
+template <class TL, int TT>
+struct StftTileSmem {
+    static constexpr int F = TL::F;
+    static constexpr int off_re = 0;
+    static constexpr int off_im = off_re + F * TL::MP;
+    static constexpr int off_slot = ((off_im + F * TL::MP + 1) / 2) * 2;          // long long [TT]
+    static constexpr int off_tile = off_slot + 2 * TT;                             // [B][TT + 1] float (x2 for complex)
+    static size_t bytes(bool complex_out) { return ((size_t)off_tile + (size_t)(TL::M + 1) * (TT + 1) * (complex_out ? 2 : 1)) * 4; }
+};
+
+template <class TL, int TT>
+__global__ void __launch_bounds__(kThreads) stft_tile_kernel(const syg::FrameArgs a) {
+    constexpr int E = TL::E, M = TL::M, G = TL::G, F = TL::F, MP = TL::MP, TTP = TT + 1;
+    static_assert(TT % F == 0 && kThreads % TT == 0, "tile geometry");
+    using SM = StftTileSmem<TL, TT>;
+    SYG_DYN_SMEM(smem_raw);
+    float* const smf = reinterpret_cast<float*>(smem_raw);
+    float* const sre = smf + SM::off_re;
+    float* const sim = smf + SM::off_im;
+    long long* const slot_off = reinterpret_cast<long long*>(smf + SM::off_slot);
+    float* const tile = smf + SM::off_tile;
+    const int tid = threadIdx.x;
+    const int f = tid / G, j = tid % G;
+    const int B = M + 1;
+    const long long n_tiles = (a.n_frames + TT - 1) / TT;
+
+    for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        for (int r0 = 0; r0 < TT; r0 += F) {
+            const int slot = r0 + f;
+            const long long gf = tl * TT + slot;
+            const bool valid = gf < a.n_frames;
+            const long long u = valid ? gf / a.T : 0;
+            const int t = valid ? (int)(gf - u * a.T) : 0;
+            UnitRef ur = unit_ref(a.g, u);
+            if (!valid) ur.valid = 0;
+            const long long p0 = (long long)t * a.hop - a.cpad;
+            if (j == 0) slot_off[slot] = valid ? ((long long)u * B) * a.T + t : -1;
+            float xr[E], xi[E];
+            SYG_UNROLL
+            for (int r = 0; r < E; ++r) {
+                const int c = j + r * G;
+                const float2 v = load_pair(a.y, ur, p0 + 2 * c, a.pad_mode);
+                const float2 w = __ldg(reinterpret_cast<const float2*>(a.window) + c);
+                xr[r] = v.x * w.x;
+                xi[r] = v.y * w.y;
+            }
+            fft_tile_forward<TL>(xr, xi, sre, sim, f, j, a.tw);
+            const int fb = f * MP;
+            SYG_UNROLL
+            for (int i = 0; i <= E / 2; ++i) {
+                const int k = j + i * G;
+                if (i == E / 2 && j != 0) break;
+                const int km = (M - k) & (M - 1);
+                const float zkr = SLD(&sre[fb + padi(k)]), zki = SLD(&sim[fb + padi(k)]);
+                const float zmr = SLD(&sre[fb + padi(km)]), zmi = SLD(&sim[fb + padi(km)]);
+                const float2 w = __ldg(&a.tws[k]);
+                float xkr, xki, xmr, xmi;
+                real_split(zkr, zki, zmr, zmi, w.x, w.y, xkr, xki, xmr, xmi);
+                const int k2 = M - k;
+                if (a.out_kind == 0) {
+                    float2* t2 = reinterpret_cast<float2*>(tile);
+                    t2[k * TTP + slot] = make_float2(xkr, xki);
+                    if (k2 != k) t2[k2 * TTP + slot] = make_float2(xmr, xmi);
+                } else {
+                    float pk_ = __fmaf_rn(xkr, xkr, xki * xki), pm_ = __fmaf_rn(xmr, xmr, xmi * xmi);
+                    if (a.out_kind == 1) { pk_ = sqrtf(pk_); pm_ = sqrtf(pm_); }
+                    tile[k * TTP + slot] = pk_;
+                    if (k2 != k) tile[k2 * TTP + slot] = pm_;
+                }
+            }
+            __syncthreads();                                        // sre / sim are rewritten by the next round; tile complete after the last
+        }
+        // rows of TT consecutive frames per bin: thread -> (slot = tid % TT, bins tid / TT + i * kThreads / TT)
+        constexpr int KS = kThreads / TT;
+        const int sl = tid % TT, kq = tid / TT;
+        const long long off = slot_off[sl];
+        if (off >= 0) {
+            const long long dstep = (long long)KS * a.T;
+            if (a.out_kind == 0) {
+                const float2* src = reinterpret_cast<const float2*>(tile) + kq * TTP + sl;
+                float2* dst = reinterpret_cast<float2*>(a.stft_out) + off + (long long)kq * a.T;
+                for (int k = kq; k < B; k += KS, src += KS * TTP, dst += dstep) *dst = *src;
+            } else {
+                const float* src = tile + kq * TTP + sl;
+                float* dst = reinterpret_cast<float*>(a.stft_out) + off + (long long)kq * a.T;
+                for (int k = kq; k < B; k += KS, src += KS * TTP, dst += dstep) *dst = *src;
+            }
+        }
+        __syncthreads();                                            // the tile is refilled by the next one
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
 // Welch / periodogram PSD, one CTA per unit (grid-stride).  scipy.signal.welch semantics (dsp.py:495-560):
 // per sub-segment: detrend('constant') -> window -> rfft(nfft) -> |X|^2 * scale; mean over sub-segments;
 // one-sided doubling except DC / Nyquist.  Optional per-unit rms / crest / peak over the whole unit

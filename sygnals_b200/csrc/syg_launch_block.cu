@@ -1,4 +1,6 @@
 // CTA-synchronous frame kernel instantiations: STFT (all sizes) and features for n_fft 4096 / 8192, plus finalize.
+#include <cstdlib>
+
 #include "syg_launch_common.h"
 #include "syg_kernels.cuh"
 #include "syg_finalize.cuh"
@@ -25,10 +27,38 @@ static int frame_block_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st,
     return 0;
 }
 
+template <class TL, int TT>
+static int stft_tile_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
+    using SM = sygdev::StftTileSmem<TL, TT>;
+    auto kfn = sygdev::stft_tile_kernel<TL, TT>;
+    const size_t smem = SM::bytes(a.out_kind == 0);
+    static size_t opted = 0;
+    static int blocks_per_sm = 1;
+    if (smem > opted) {
+        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted = smem;
+        int nb = 0;
+        LCK(SYG_OCCUPANCY(nb, kfn, sygdev::kThreads, smem));
+        if (nb < 1) { err = "stft tile kernel does not fit on an SM"; return -3; }
+        blocks_per_sm = nb;
+    }
+    const long long n_tiles = (a.n_frames + TT - 1) / TT;
+    if (n_tiles <= 0) return 0;
+    const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * blocks_per_sm);
+    SYG_LAUNCH(kfn, grid, sygdev::kThreads, smem, st, a);
+    LCK(cudaGetLastError());
+    return 0;
+}
+
 int frame_block(int n_fft, int mode, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using namespace sygdev;
     const int l = ilog2i(n_fft / 2);
     if (mode == MODE_STFT) {
+        static int env = -1;                                            // SYGB200_STFT_BLOCK=1: the per-frame-store kernel (comparison)
+        if (env < 0) { const char* e = std::getenv("SYGB200_STFT_BLOCK"); env = e ? std::atoi(e) : 0; }
+        if (!env && l == 11) return stft_tile_t<FftTile<11, 16>, 8>(a, sm_count, st, err);
+        if (!env && l == 12) return a.out_kind == 0 ? stft_tile_t<FftTile<12, 16>, 4>(a, sm_count, st, err)
+                                                     : stft_tile_t<FftTile<12, 16>, 8>(a, sm_count, st, err);
         switch (l) {
             case 4: return frame_block_t<FftTile<4, 4>, MODE_STFT>(a, sm_count, st, err);
             case 5: return frame_block_t<FftTile<5, 8>, MODE_STFT>(a, sm_count, st, err);
