@@ -162,15 +162,27 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, std::function<void()> body)
         b.fibers.resize(nthreads);
         b.warps.resize((nthreads + 31) / 32);
         for (auto& f : b.fibers) f.stack = (char*)std::malloc(kStack);
-        b.dyn = (unsigned char*)std::aligned_alloc(1024, ((smem + 1023) / 1024 + 1) * 1024);
+        // dynamic shared memory with guard zones on both sides: filled with 0xFF (a NaN pattern as float, so a stray read poisons
+        // the result and the parity tests notice) and checked after every block (a stray write aborts)
+        constexpr size_t kGuard = 4096;
+        const size_t span = ((smem + 15) / 16) * 16;
+        unsigned char* raw = (unsigned char*)std::aligned_alloc(1024, ((kGuard + span + kGuard + 1023) / 1024) * 1024);
+        std::memset(raw, 0xFF, kGuard + span + kGuard);
+        b.dyn = raw + kGuard;
         std::function<void()> local_body = body;
         for (;;) {
             unsigned bid = next.fetch_add(1);
             if (bid >= nblocks) break;
             run_block(b, grid, block, bid, local_body, reverse);
+            for (size_t i = 0; i < kGuard; ++i) {
+                if (raw[i] != 0xFF || raw[kGuard + span + i] != 0xFF) {
+                    std::fprintf(stderr, "sygemu: block %u wrote outside its %zu bytes of dynamic shared memory (guard byte %zu)\n", bid, smem, i);
+                    std::abort();
+                }
+            }
         }
         for (auto& f : b.fibers) std::free(f.stack);
-        std::free(b.dyn);
+        std::free(raw);
         g_blk = nullptr;
     };
     if (nworkers <= 1) {
