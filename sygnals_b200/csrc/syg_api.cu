@@ -169,16 +169,14 @@ int get_window(syg_ctx* ctx, int window, int win_length, int n_fft, bool centred
 // failures as a negative SYG_E_* code plus a message.
 int launch_rc(int rc, const std::string& err) { return rc == SYG_OK ? SYG_OK : fail(rc, "%s", err.c_str()); }
 
-// stage: 0 fused kernel, 1 / 2 the two-stage launch of the warp kernel (n_fft <= 2048 only)
-int launch_features(int n_fft, int stage, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
+int launch_features(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
     std::string err;
     if (n_fft > 2048) return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_FEATURES, a, sm_count, st, err), err);
     constexpr unsigned extra = syg::FB_BANDWIDTH | syg::FB_FLATNESS | syg::FB_DOMINANT | syg::FB_MEAN_AMP | syg::FB_STD_AMP;
-    return launch_rc(syglaunch::frame_warp(n_fft, (a.mask & extra) != 0, stage, a, sm_count, st, err), err);
+    return launch_rc(syglaunch::frame_warp(n_fft, (a.mask & extra) != 0, a, sm_count, st, err), err);
 }
 
-// words per spectrum of the warp kernel (= WarpTile::PS) and frames per warp task (= WarpTile::FW)
-int warp_ps_words(int n_fft) { const int nb = n_fft / 2 + 1; return ((nb + 4 * (nb >> 5) + 48 + 3) / 4) * 4; }
+// frames per warp task of the warp kernel (= WarpTile::FW)
 int warp_fw(int n_fft) {
     switch (ilog2i(n_fft / 2)) { case 4: return 8; case 5: return 8; case 6: return 4; case 7: return 4; case 8: return 2; case 9: return 2; default: return 1; }
 }
@@ -222,8 +220,7 @@ struct FeaturePlan {
     syg::FinalizeArgs fin;
     int n_rows = 0;
     int T = 0;
-    size_t ws_per_unit = 0;        // bytes of melws + cws (+ spectra when two-stage) per unit
-    bool two_stage = false;        // warp kernel as FFT launch + epilogue launch (spectra through an L2-sized workspace)
+    size_t ws_per_unit = 0;        // bytes of melws + cws per unit
     int n_fft = 0;
     int entropy_bins = 10;
 };
@@ -372,18 +369,6 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
     pl.entropy_bins = p->entropy_bins;
     if ((mask & syg::FB_ENTROPY) && (p->entropy_bins < 1 || p->entropy_bins > 16))
         return fail(SYG_E_UNSUPPORTED, "signal_entropy num_bins=%d: supported range is [1, 16]", p->entropy_bins);
-    {
-        // two-stage launch: worth it when the epilogues dominate (they are latency bound and run at twice the occupancy on
-        // their own); SYGB200_TWO_STAGE=0/1 overrides
-        static int env = -1;
-        if (env < 0) { const char* e = std::getenv("SYGB200_TWO_STAGE"); env = e ? (std::atoi(e) ? 1 : 0) : 2; }
-        const bool heavy = (mask & syg::FB_CONTRAST) != 0 || ((mask & syg::FB_MFCC) != 0 && (mask & syg::FB_SPECSTATS) != 0);
-        (void)heavy;
-        // measured on B200 (cfg4): two stages win 4 % at 1 GiB chunks and lose 10-40 % at L2-sized chunks (launch tails), and
-        // they move 8 KB of spectrum per frame through HBM -> the fused kernel stays the default
-        pl.two_stage = fl <= 2048 && (mask & syg::FB_SPECTRUM_ANY) != 0 && env == 1;
-        if (pl.two_stage) ws += (size_t)(T + warp_fw(fl)) * warp_ps_words(fl) * sizeof(float);
-    }
     pl.ws_per_unit = ws + 4 * sizeof(unsigned);
     pl.fin.T = (int)T;
     pl.fin.n_rows = rows;
@@ -406,8 +391,6 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
     a.melws = reinterpret_cast<float*>(w + off);
     off += ((size_t)a.n_frames * pl.fin.n_mels * sizeof(float) + 255) / 256 * 256;
     a.cws = reinterpret_cast<float*>(w + off);
-    off += ((size_t)a.n_frames * 2 * pl.fin.nb * sizeof(float) + 255) / 256 * 256;
-    a.pws = reinterpret_cast<float*>(w + off);
     const bool need_fin = (a.mask & (syg::FB_MFCC | syg::FB_CONTRAST)) != 0;
     if (need_fin) CK(cudaMemsetAsync(a.unit_max, 0, (size_t)g.n_units * 4 * sizeof(unsigned), st));
     int rc = SYG_OK;
@@ -418,17 +401,9 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
         if (trc) return fail(trc, "%s", err.c_str());
     }
     if ((a.mask & ~syg::FB_TIME_EXTRA) == 0) return SYG_OK;             // nothing for the frame kernels
-    if (pl.two_stage) {
-        {
-            ProfScope ps(ctx, st, PROF_FRAME);
-            rc = launch_features(n_fft, 1, a, ctx->sm_count, st);
-        }
-        if (rc) return rc;
+    {
         ProfScope ps(ctx, st, PROF_FRAME);
-        rc = launch_features(n_fft, 2, a, ctx->sm_count, st);
-    } else {
-        ProfScope ps(ctx, st, PROF_FRAME);
-        rc = launch_features(n_fft, 0, a, ctx->sm_count, st);
+        rc = launch_features(n_fft, a, ctx->sm_count, st);
     }
     if (rc) return rc;
     if (need_fin) {
@@ -456,7 +431,6 @@ size_t features_ws_bytes(const FeaturePlan& pl, long long n) {
     size_t b = ((size_t)n * 4 * sizeof(unsigned) + 255) / 256 * 256;
     b += ((size_t)n * pl.T * pl.fin.n_mels * sizeof(float) + 255) / 256 * 256;
     b += ((size_t)n * pl.T * 2 * pl.fin.nb * sizeof(float) + 255) / 256 * 256;
-    if (pl.two_stage) b += ((size_t)n * pl.T + warp_fw(pl.n_fft)) * warp_ps_words(pl.n_fft) * sizeof(float);
     return b + 256;
 }
 

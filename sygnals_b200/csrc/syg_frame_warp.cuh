@@ -76,11 +76,11 @@ SYG_DEVICE SYG_INLINE double lanes_scan_incl(double v, int gl) {
     return v;
 }
 
-// STAGE 0: fused (framing -> FFT -> |X|^2 in shared memory -> all epilogues).
-// STAGE 1 + STAGE 2: the same code as two launches.  Stage 1 (FFT, 128 registers, 16 warps/SM) stores |X|^2 to a workspace
-// that the host sizes to stay in L2; stage 2 (epilogues, 64 registers, 32 warps/SM) stages it into shared memory.  The
-// epilogues are latency bound (serial REDUX pops, min/max networks, dependent loads): twice the resident warps hide what the
-// fused kernel's 4 warps per scheduler cannot.  (CTA barriers between phases were measured and rejected: +8 %.)
+// STAGE 0: features (framing -> FFT -> |X|^2 in shared memory -> all epilogues).
+// STAGE 3: STFT output (framing -> FFT -> real split -> transposed CTA tile -> contiguous row stores).
+// (A two-launch variant -- FFT kernel + 64-register epilogue kernel with the spectra handed over through a workspace -- was
+// measured and removed: +4 % at best, see DESIGN.md 4.1 and profiles/r01_t_two_stage_ncu_summary.txt.  CTA barriers between
+// the phases of the fused kernel were measured too: +8 % time.)
 template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameArgs a) {
     using WT = WarpTile<TL, NT>;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int f = lane / G, j = lane % G;
-    constexpr int RSS = (STAGE == 2) ? PS : WT::RS;                   // floats per frame region of this launch
+    constexpr int RSS = WT::RS;                                       // floats per frame region
     constexpr int WF = FW * RSS;                                      // floats per warp
     float* const wbase = reinterpret_cast<float*>(smem_raw) + warp * WF;
     // STAGE 3 (STFT output): CTA tile [B][TT + 1] behind the warps' regions, TT = frames of one CTA round; + per-slot output offsets
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     float* const tile = reinterpret_cast<float*>(slot_off + TT);                                                    // [B][TTP] float or float2
     float* const pww = wbase;                                         // [FW][RSS]  Z (float2, zpad layout), later |X|^2 (ppad layout)
     float2* const zs = reinterpret_cast<float2*>(wbase + f * RSS);
-    float* pf = wbase + f * RSS;
+    float* const pf = wbase + f * RSS;
 
     // pad / slack words of the spectra are read (with zero weight) by the mel sweep: they must never hold NaN patterns
     for (int i = lane; i < WF; i += 32) wbase[i] = 0.0f;
@@ -159,8 +159,6 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         const long long p0 = (long long)t * a.hop - a.cpad;
 
         float* const orow = a.out + (long long)u * a.n_rows * a.T + t;
-        if (STAGE != 2) {
-        if (STAGE == 1) pf = a.pws + gf * PS;                            // stage 1: the spectrum goes to the workspace (rows exist for every task frame)
         // ---------------- framing + window + time-domain partial statistics ----------------
         float2 z[E];
         float2 sq2 = make_float2(0.0f, 0.0f);
@@ -358,25 +356,6 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             }
         }
 
-        }  // STAGE != 2
-        if (STAGE == 2) {                                                // stage 2: bring the task's spectra into shared memory
-            SYG_UNROLL
-            for (int ff = 0; ff < FW; ++ff) {
-                const float4* src = reinterpret_cast<const float4*>(a.pws + (task * FW + ff) * PS);
-                float4* dst = reinterpret_cast<float4*>(pww + ff * RSS);
-                constexpr int IM = (M + ((M >> 5) << 2)) / 4;            // float4 that holds bin M (its first word)
-                for (int i = lane; i < PS / 4; i += 32) {
-                    // the workspace's pad and slack words are never written: they read as zeros here (the mel sweep multiplies
-                    // them by zero weights, which must not meet NaN patterns)
-                    float4 v = __ldg(src + i);
-                    if (i % 9 == 8 || i > IM) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    else if (i == IM) { v.y = 0.0f; v.z = 0.0f; v.w = 0.0f; }
-                    dst[i] = v;
-                }
-            }
-            __syncwarp();
-        }
-        if (STAGE != 1) {
         // ---------------- per-frame spectral statistics (lane j owns bins [j*E, j*E+E), last lane also bin M) ----------------
         if (a.mask & syg::FB_SPECSTATS) {
             const int k0 = j * E;
@@ -580,7 +559,6 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 }
             }
         }
-        }  // STAGE != 1
         __syncwarp();                                                   // smem slices are reused by the next task
     }
 }

@@ -1,4 +1,4 @@
-// warp-synchronous feature kernel instantiations (n_fft <= 2048), fused, EXTRA=false
+// warp-synchronous feature kernel instantiations (n_fft <= 2048), EXTRA=false
 #include "syg_launch_warp.h"
 
 namespace syglaunch {

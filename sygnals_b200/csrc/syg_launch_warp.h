@@ -8,14 +8,14 @@
 
 namespace syglaunch {
 
-// STAGE 0: fused kernel; 1: FFT -> spectra workspace; 2: spectra workspace -> features (see syg_frame_warp.cuh)
+// STAGE 0: features; 3: STFT output (see syg_frame_warp.cuh)
 template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using WT = sygdev::WarpTile<TL, NT>;
     static int blocks_per_sm[2] = {0, 0};
     static size_t smem_seen[2] = {0, 0};
     auto kfn = sygdev::frame_warp_kernel<TL, EXTRA, NT, MINB, STAGE>;
-    size_t smem = (size_t)WT::kWarps * WT::FW * (STAGE == 2 ? WT::PS : WT::RS) * sizeof(float);
+    size_t smem = (size_t)WT::kWarps * WT::FW * WT::RS * sizeof(float);
     const int wide = (STAGE == 3 && a.out_kind == 0) ? 1 : 0;        // complex64 tile
     if (STAGE == 0) smem += WT::table_bytes(a.n_mels, (a.mask & syg::FB_MFCC) ? a.mel_pw_f4 : 0);
     if (STAGE == 3) {
@@ -42,7 +42,7 @@ static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, 
 template <bool EXTRA, int STAGE>
 static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using namespace sygdev;
-    constexpr int MINB = (STAGE == 2) ? 4 : 2;          // stage 2: 64 registers, 32 warps per SM
+    constexpr int MINB = 2;
     switch (ilog2i(n_fft / 2)) {
         case 4: return frame_warp_t<FftTile<4, 4>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
         case 5: return frame_warp_t<FftTile<5, 8>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
@@ -51,7 +51,7 @@ static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count,
         case 8: return frame_warp_t<FftTile<8, 16>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
         case 9: return frame_warp_t<FftTile<9, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
         case 10:
-            // fused: one CTA of 16 warps per SM so that the 38 KB of plan tables are held once (leaves ~50 KB of L1)
+            // features: one CTA of 16 warps per SM so that the 38 KB of plan tables are held once (leaves ~50 KB of L1)
             if (STAGE == 0) return frame_warp_t<FftTile<10, 32>, EXTRA, 512, 1, STAGE>(a, sm_count, st, err);
             return frame_warp_t<FftTile<10, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
     }

@@ -74,7 +74,6 @@ struct FrameArgs {
     float* cws;                 // [n_frames][2*nb]     contrast peaks | valleys (linear)
     unsigned* unit_max;         // [n_units][4]         bit images of max mel energy, max peak, max valley
     int mel_pw_f4;              // float4 count of mel_pw (for the shared-memory copy of the plan tables)
-    float* pws;                 // two-stage launch only: [n_frames][PS] power spectra (ppad layout) handed from stage 1 to stage 2
     // ---- stft
     int out_kind;               // 0 complex64, 1 magnitude, 2 power
     void* stft_out;             // [n_units][B][T]
