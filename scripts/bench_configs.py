@@ -33,7 +33,7 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg5"]
+    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg5"]      # add "yardstick" for the torch/torchaudio library lines
     if "cfg2" in which:
         sr, n, L = 16000, 4096, 16000
         clips = torch.empty((n, L), dtype=torch.float32, device="cuda")
@@ -46,6 +46,14 @@ def main():
                               "audio_s_per_s": n * 1.0 / (ms * 1e-3), "alg_GB": by / 1e9, "GBps": by / ms / 1e6,
                               "hbm_frac": by / ms / 1e6 / peak}), flush=True)
             del out
+            if "yardstick" in which:
+                # in-image GPU LIBRARY yardstick: torch.stft (cuFFT) + abs on the same clips -- not the reference, not this engine
+                win = torch.hann_window(n_fft, periodic=True, device="cuda")
+                lib = lambda: torch.stft(clips, n_fft, hop_length=n_fft // 4, win_length=n_fft, window=win, center=True,
+                                         pad_mode="constant", return_complex=True).abs()
+                ms_l = timed(lib)
+                print(json.dumps({"config": "cfg2 yardstick torch.stft(cuFFT).abs()", "n_fft": n_fft, "ms": ms_l,
+                                  "audio_s_per_s": n * 1.0 / (ms_l * 1e-3), "engine_speedup": ms_l / ms}), flush=True)
         del clips
     if "cfg3" in which:
         sr, n, L = 16000, 100000, 16000
@@ -58,6 +66,19 @@ def main():
         print(json.dumps({"config": "cfg3 speech-commands mfcc13 (n_fft 512 hop 160, 40 mels)", "clips": n, "ms": ms,
                           "audio_s_per_s": n * 1.0 / (ms * 1e-3), "alg_GB": by / 1e9, "GBps": by / ms / 1e6,
                           "hbm_frac": by / ms / 1e6 / peak}), flush=True)
+        if "yardstick" in which:
+            # library yardstick: torchaudio MFCC (cuFFT STFT -> dense mel matmul -> global-ref dB -> DCT matmul); its dB reference
+            # and top_db handling differ slightly from librosa's per-call ref=np.max, so this is a speed yardstick only
+            import torchaudio
+            tf = torchaudio.transforms.MFCC(sample_rate=sr, n_mfcc=13, log_mels=False,
+                                            melkwargs={"n_fft": 512, "hop_length": 160, "n_mels": 40, "center": True, "pad_mode": "constant",
+                                                       "norm": "slaney", "mel_scale": "slaney"}).to("cuda")
+            def lib():
+                for i in range(0, n, 25000):             # 4 chunks: the library materialises complex spectra (257 x 101 x 8 B per clip)
+                    tf(clips[i:i + 25000])
+            ms_l = timed(lib)
+            print(json.dumps({"config": "cfg3 yardstick torchaudio.transforms.MFCC (4 chunks of 25k clips)", "ms": ms_l,
+                              "audio_s_per_s": n * 1.0 / (ms_l * 1e-3), "engine_speedup": ms_l / ms}), flush=True)
         del clips, out
     if "cfg5" in which:
         fs, ch, seconds = 25600, 64, 600

@@ -28,21 +28,23 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(p) <= t for p in _deps())
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """``defines``/``out``: experiment builds (A/B variants of a kernel) into a separate object directory and library file."""
+    objdir = OBJDIR if out == OUT else OBJDIR + "_" + os.path.basename(out)
+    if not force and out == OUT and up_to_date():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libsygb200.so cannot be built (there is no CPU fallback)")
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     from concurrent.futures import ThreadPoolExecutor
     hdr_t = max(os.path.getmtime(p) for p in _deps() if not p.endswith(".cu"))
 
     def compile_one(src):
-        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(hdr_t, os.path.getmtime(src)):
             return obj, ""
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
@@ -53,13 +55,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT + ".tmp"] + [o for o, _ in results]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out + ".tmp"] + [o for o, _ in results]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
-    os.replace(OUT + ".tmp", OUT)
-    return OUT
+    os.replace(out + ".tmp", out)
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=os.path.abspath(outs[0]) if outs else OUT))

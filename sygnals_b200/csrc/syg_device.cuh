@@ -604,6 +604,8 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
         // one element per step and direction (the lowest lane holding the extreme pops), both directions in one
         // straight-line body: two independent REDUX chains for the scheduler to interleave
         const unsigned lt = (1u << lane) - 1u;
+        // (bulk rounds -- pop every head above the warp maximum of the second keys at once, ~7 per round -- were measured:
+        // two more REDUX per round cost more than the saved rounds, +1.3 % kernel time.  Rejected.)
 #ifndef SYG_EMU
 #pragma unroll 1
 #endif
