@@ -1,6 +1,6 @@
 # A/B of two builds of the library on one box: the in-tree libsygb200.so against build/alt/$ALT (an experiment build made with
 # `python -m sygnals_b200.build -DNAME=VALUE --out=build/alt/<file>.so`); alternates the two REPS times to average out drift
-ALT=${ALT:?name of the library under build/alt}
+ALT=${ALT:?names of the libraries under build/alt}
 cp sygnals_b200/libsygb200.so /tmp/lib_main.so
 line() { python bench.py --hours ${HOURS:-2} --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "
 import sys, json
@@ -10,6 +10,6 @@ for ln in sys.stdin:
 "; }
 for i in $(seq ${REPS:-3}); do
   cp /tmp/lib_main.so sygnals_b200/libsygb200.so; line main
-  cp build/alt/$ALT sygnals_b200/libsygb200.so; line "$ALT"
+  for a in $ALT; do cp build/alt/$a sygnals_b200/libsygb200.so; line "$a"; done
 done
 cp /tmp/lib_main.so sygnals_b200/libsygb200.so
