@@ -376,26 +376,42 @@ __global__ void __launch_bounds__(kThreads) stft_tile_kernel(const syg::FrameArg
     const int B = M + 1;
     const long long n_tiles = (a.n_frames + TT - 1) / TT;
 
+    // One CTA per SM (the tile fills shared memory), so nothing else hides the latency of a frame's global loads and most of
+    // the register file is idle: the frame-invariant operands (this thread's window taps and split twiddles) stay in registers
+    // for the whole kernel and the NEXT frame's samples are fetched while the current frame is transformed.
+    float2 wreg[E];
+    SYG_UNROLL
+    for (int r = 0; r < E; ++r) wreg[r] = __ldg(reinterpret_cast<const float2*>(a.window) + j + r * G);
+    float2 twsreg[E / 2 + 1];
+    SYG_UNROLL
+    for (int i = 0; i <= E / 2; ++i) twsreg[i] = (i < E / 2 || j == 0) ? __ldg(&a.tws[j + i * G]) : make_float2(0.0f, 0.0f);
+    float2 vn[E];                                                   // samples of the frame this thread group transforms next
+    long long off_n = -1;                                           // its output offset (u, bin 0, t), -1 = past the end
+    auto fetch = [&](long long gf) {
+        const bool valid = gf < a.n_frames;
+        const long long u = valid ? gf / a.T : 0;
+        const int t = valid ? (int)(gf - u * a.T) : 0;
+        UnitRef ur = unit_ref(a.g, u);
+        if (!valid) ur.valid = 0;
+        const long long p0 = (long long)t * a.hop - a.cpad;
+        SYG_UNROLL
+        for (int r = 0; r < E; ++r) vn[r] = load_pair(a.y, ur, p0 + 2 * (j + r * G), a.pad_mode);
+        off_n = valid ? ((long long)u * B) * a.T + t : -1;
+    };
+    fetch((long long)blockIdx.x * TT + f);
+
     for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
         for (int r0 = 0; r0 < TT; r0 += F) {
             const int slot = r0 + f;
-            const long long gf = tl * TT + slot;
-            const bool valid = gf < a.n_frames;
-            const long long u = valid ? gf / a.T : 0;
-            const int t = valid ? (int)(gf - u * a.T) : 0;
-            UnitRef ur = unit_ref(a.g, u);
-            if (!valid) ur.valid = 0;
-            const long long p0 = (long long)t * a.hop - a.cpad;
-            if (j == 0) slot_off[slot] = valid ? ((long long)u * B) * a.T + t : -1;
+            if (j == 0) slot_off[slot] = off_n;
             float xr[E], xi[E];
             SYG_UNROLL
             for (int r = 0; r < E; ++r) {
-                const int c = j + r * G;
-                const float2 v = load_pair(a.y, ur, p0 + 2 * c, a.pad_mode);
-                const float2 w = __ldg(reinterpret_cast<const float2*>(a.window) + c);
-                xr[r] = v.x * w.x;
-                xi[r] = v.y * w.y;
+                xr[r] = vn[r].x * wreg[r].x;
+                xi[r] = vn[r].y * wreg[r].y;
             }
+            // prefetch: next round of this tile, or the first round of this CTA's next tile (frames past the end load nothing)
+            fetch((r0 + F < TT) ? tl * TT + (r0 + F + f) : (tl + gridDim.x) * TT + f);
             fft_tile_forward<TL>(xr, xi, sre, sim, f, j, a.tw);
             const int fb = f * MP;
             SYG_UNROLL
@@ -405,7 +421,7 @@ __global__ void __launch_bounds__(kThreads) stft_tile_kernel(const syg::FrameArg
                 const int km = (M - k) & (M - 1);
                 const float zkr = SLD(&sre[fb + padi(k)]), zki = SLD(&sim[fb + padi(k)]);
                 const float zmr = SLD(&sre[fb + padi(km)]), zmi = SLD(&sim[fb + padi(km)]);
-                const float2 w = __ldg(&a.tws[k]);
+                const float2 w = twsreg[i];
                 float xkr, xki, xmr, xmi;
                 real_split(zkr, zki, zmr, zmi, w.x, w.y, xkr, xki, xmr, xmi);
                 const int k2 = M - k;
