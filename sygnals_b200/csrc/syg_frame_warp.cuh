@@ -185,19 +185,30 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     z[r] = __fmul2_rn(v, w);
                 }
             } else {
-                // edge / unaligned frames: per-sample predicated loads (zero padding by predicate; reflect padding for STFT)
-                const float* yb = a.y + ur.start;
+                // edge / unaligned frames: predicated loads (zero padding by predicate; reflect padding for STFT).  The frame's valid
+                // range is computed once in frame-local 32-bit coordinates [lo, lo + span): one unsigned compare per sample; pairs
+                // that lie fully inside an 8-byte aligned frame still load as one LDG.64.
                 const long long nv = ur.valid;
                 const bool refl = (STAGE == 3) && a.pad_mode == 1 && nv > 0;
+                const float* const fb = a.y + ur.start + p0;             // frame base: dereferenced at valid positions only
+                const long long lo64 = p0 < 0 ? -p0 : 0, hi64 = nv - p0;
+                const int lo = (int)(lo64 < 2 * M ? lo64 : 2 * M);
+                const int hi = (int)(hi64 < 0 ? 0 : (hi64 < 2 * M ? hi64 : 2 * M));
+                const unsigned span = hi > lo ? (unsigned)(hi - lo) : 0u;
+                const bool al = (reinterpret_cast<uintptr_t>(fb) & 7u) == 0;
                 SYG_UNROLL
                 for (int r = 0; r < E; ++r) {
                     const int c = j + r * G;
-                    const long long pos = p0 + 2 * c;
+                    const unsigned d = (unsigned)(2 * c - lo);
                     float2 v = make_float2(0.0f, 0.0f);
-                    if (pos >= 0 && pos < nv) v.x = __ldg(yb + pos);
-                    else if (refl) v.x = __ldg(yb + reflect_index(pos, nv));
-                    if (pos + 1 >= 0 && pos + 1 < nv) v.y = __ldg(yb + pos + 1);
-                    else if (refl) v.y = __ldg(yb + reflect_index(pos + 1, nv));
+                    if (al && d < span && d + 1u < span) {
+                        v = __ldg(reinterpret_cast<const float2*>(fb) + c);
+                    } else {
+                        if (d < span) v.x = __ldg(fb + 2 * c);
+                        else if (refl) v.x = __ldg(a.y + ur.start + reflect_index(p0 + 2 * c, nv));
+                        if (d + 1u < span) v.y = __ldg(fb + 2 * c + 1);
+                        else if (refl) v.y = __ldg(a.y + ur.start + reflect_index(p0 + 2 * c + 1, nv));
+                    }
                     const float2 w = TBL ? w2[c] : __ldg(w2 + c);
                     sq2 = __ffma2_rn(v, v, sq2);
                     pk = fmaxf(pk, fabsf(v.x));
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                         if (k2 != k) t2[k2 * TTP + slot] = make_float2(xmr, xmi);
                     } else {
                         float pk_ = __fmaf_rn(xkr, xkr, xki * xki), pm_ = __fmaf_rn(xmr, xmr, xmi * xmi);
-                        if (a.out_kind == 1) { pk_ = sqrtf(pk_); pm_ = sqrtf(pm_); }
+                        if (a.out_kind == 1) { pk_ = sqrt_approx(pk_); pm_ = sqrt_approx(pm_); }   // MUFU.SQRT: 1 ulp, one instruction (sqrtf is ~8)
                         tile[k * TTP + slot] = pk_;
                         if (k2 != k) tile[k2 * TTP + slot] = pm_;
                     }

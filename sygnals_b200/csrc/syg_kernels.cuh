@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kThreads) frame_kernel(const syg::FrameArgs a)
                     } else {
                         float* o = reinterpret_cast<float*>(a.stft_out);
                         float pk_ = __fmaf_rn(xkr, xkr, xki * xki), pm_ = __fmaf_rn(xmr, xmr, xmi * xmi);
-                        if (a.out_kind == 1) { pk_ = sqrtf(pk_); pm_ = sqrtf(pm_); }
+                        if (a.out_kind == 1) { pk_ = sqrt_approx(pk_); pm_ = sqrt_approx(pm_); }   // MUFU.SQRT: 1 ulp, one instruction (sqrtf is ~8)
                         o[ob + (long long)k * a.T] = pk_;
                         if (k2 != k) o[ob + (long long)k2 * a.T] = pm_;
                     }
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kThreads) stft_tile_kernel(const syg::FrameArg
                     if (k2 != k) t2[k2 * TTP + slot] = make_float2(xmr, xmi);
                 } else {
                     float pk_ = __fmaf_rn(xkr, xkr, xki * xki), pm_ = __fmaf_rn(xmr, xmr, xmi * xmi);
-                    if (a.out_kind == 1) { pk_ = sqrtf(pk_); pm_ = sqrtf(pm_); }
+                    if (a.out_kind == 1) { pk_ = sqrt_approx(pk_); pm_ = sqrt_approx(pm_); }   // MUFU.SQRT: 1 ulp, one instruction (sqrtf is ~8)
                     tile[k * TTP + slot] = pk_;
                     if (k2 != k) tile[k2 * TTP + slot] = pm_;
                 }
