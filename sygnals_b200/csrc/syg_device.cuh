@@ -567,13 +567,20 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
     float2 r;
     if (n == 1) {                                               // extremes of the band
         unsigned mx = 0u, mn = 0xffffffffu;
+        if (count <= 64) {                                      // the usual case (low octave bands): two predicated loads, no loop
+            const bool h0 = lane < count, h1 = lane + 32 < count;
+            const unsigned x0 = h0 ? __float_as_uint(q[0]) : 0u, x1 = h1 ? __float_as_uint(q[36]) : 0u;
+            mx = max(x0, x1);
+            mn = min(h0 ? x0 : 0xffffffffu, h1 ? x1 : 0xffffffffu);
+        } else {
 #ifndef SYG_EMU
 #pragma unroll 1
 #endif
-        for (int i = 0; i < mine; ++i) {
-            const unsigned x = __float_as_uint(q[36 * i]);
-            mx = max(mx, x);
-            mn = min(mn, x);
+            for (int i = 0; i < mine; ++i) {
+                const unsigned x = __float_as_uint(q[36 * i]);
+                mx = max(mx, x);
+                mn = min(mn, x);
+            }
         }
         r.x = sqrt_approx(__uint_as_float(__reduce_max_sync(kFull, mx)));
         r.y = sqrt_approx(__uint_as_float(__reduce_min_sync(kFull, mn)));
@@ -663,9 +670,8 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
             }
         }
     }
-    const float inv_n = 1.0f / (float)n;
-    r.x = sa * inv_n;
-    r.y = sb * inv_n;
+    r.x = __fdividef(sa, (float)n);                             // MUFU.RCP + FMUL (2 ulp; the parity bar is 1e-3 dB)
+    r.y = __fdividef(sb, (float)n);
     return r;
 }
 

@@ -552,16 +552,15 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 if (gff >= a.n_frames) break;
                 const float* pp = pww + ff * RSS;
                 float pmx = 0.0f, vmx = 0.0f;
+                float mine_pv = 0.0f;                                   // lane bd keeps band bd's peak, lane nb + bd its valley
                 for (int bd = 0; bd < a.nb; ++bd) {
                     float peak, valley;
                     band_peak_valley_any(pp, a.band_lo[bd], a.band_cnt[bd], a.band_n[bd], peak, valley);
-                    if (lane == 0) {
-                        a.cws[gff * (2 * a.nb) + bd] = peak;
-                        a.cws[gff * (2 * a.nb) + a.nb + bd] = valley;
-                    }
-                    if (peak == peak) pmx = fmaxf(pmx, peak);
-                    if (valley == valley) vmx = fmaxf(vmx, valley);
+                    mine_pv = (lane == bd) ? peak : ((lane == a.nb + bd) ? valley : mine_pv);
+                    pmx = fmaxf(pmx, peak);                             // fmaxf drops the NaN of an empty band
+                    vmx = fmaxf(vmx, valley);
                 }
+                if (lane < 2 * a.nb) a.cws[gff * (2 * a.nb) + lane] = mine_pv;   // one coalesced store per frame (nb <= kMaxBands = 12)
                 const long long uff = __shfl_sync(kFull, u, ff * G);    // unit of frame ff (all lanes take part)
                 if (lane == 0) {
                     unsigned* um = a.unit_max + uff * 4;
