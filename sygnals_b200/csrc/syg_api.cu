@@ -414,7 +414,7 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
         f.cws = a.cws;
         f.unit_max = a.unit_max;
         f.out = out;
-        const size_t smem = (size_t)sygdev::kFinTT * (f.n_mels + 3) * sizeof(double);   // two folded halves (or one full tile) + padding
+        const size_t smem = (size_t)sygdev::kFinTT * sygdev::fin_pitch(f.n_mels) * sizeof(float);     // FP32 S_db tile
         const long long n_tiles = (g.n_units * (long long)pl.T + sygdev::kFinTT - 1) / sygdev::kFinTT;
         static int fin_cap = -1;                                      // SYGB200_FIN_CTAS: CTAs per SM of the finalize grid (0 = one CTA per tile)
         if (fin_cap < 0) { const char* e = std::getenv("SYGB200_FIN_CTAS"); fin_cap = e ? std::atoi(e) : 0; }

@@ -23,6 +23,23 @@ SYG_DEVICE SYG_INLINE float db10(float x) {
 #endif
 }
 
+// D (8x8) += A (8x4, row major) * B (4x8, column major) on the FP64 tensor cores.  Fragments (PTX ISA, mma.m8n8k4 .f64), with
+// g = lane / 4 and q = lane % 4: a = A[g][q], b = B[q][g], {d0, d1} = D[g][2q], D[g][2q + 1].
+SYG_DEVICE SYG_INLINE void mma_m8n8k4_f64(double& d0, double& d1, double av, double bv) {
+#ifdef SYG_EMU
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    for (int k = 0; k < 4; ++k) {
+        const double ak = __shfl_sync(kFull, av, g * 4 + k);
+        const double b0 = __shfl_sync(kFull, bv, (2 * q) * 4 + k), b1 = __shfl_sync(kFull, bv, (2 * q + 1) * 4 + k);
+        d0 = fma(ak, b0, d0);
+        d1 = fma(ak, b1, d1);
+    }
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(av), "d"(bv));
+#endif
+}
+
 // Persistent: the chunk's frames are one flat sequence cut into tiles of kFinTT consecutive frames (a tile may straddle units:
 // every slot carries its own unit, reference level and clamps), CTAs stride over the tiles.  Short units (T = 101 in the
 // speech-commands shape) no longer leave partial tiles or one tiny CTA per 32 frames.
@@ -35,9 +52,10 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeA
     const long long n_tiles = (total + kFinTT - 1) / kFinTT;
     const int N = a.n_mels;
     const int H = a.dct_fold ? (N + 1) / 2 : N;
-    const int ld = H + 1;
-    double* const se = reinterpret_cast<double*>(smem_raw);            // [kFinTT][H + 1]
-    double* const so = a.dct_fold ? se + kFinTT * ld : se;
+    const int H4 = (H + 3) / 4 * 4;                                     // DMMA k-steps of 4 columns
+    const int P = fin_pitch(N);
+    float* const xs = reinterpret_cast<float*>(smem_raw);              // [kFinTT][P] S_db (FP32, as the reference's float32->float64 values)
+    const int warp = tid >> 5, lane = tid & 31;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long gf0 = tile * kFinTT;
@@ -57,59 +75,89 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeA
         }
         __syncthreads();
         if (a.row_mfcc >= 0) {
-            // S_db tile in float64: the DCT accumulates in FP64 (|sum| reaches 80*sqrt(n_mels) ~ 905 and the parity bar is 1e-3
-            // absolute).  DCT-II rows are (-1)^k symmetric about the centre (cos(pi k (2(N-1-n)+1) / 2N) = (-1)^k cos(pi k (2n+1) / 2N)),
-            // so the tile is stored folded: se[n] = s[n] + s[N-1-n], so[n] = s[n] - s[N-1-n] (n < N/2; centre term of an odd N
-            // separately) and every coefficient needs H = ceil(N/2) products.  Other DCT types use the unfolded tile (se = so = s).
-            for (int i = tid; i < nt * H; i += kThreads) {
-                const int tt = i / H, n = i - tt * H;
-                const float* row = a.melws + (gf0 + tt) * N;
-                const float ref_db = s_ref[tt], floor_db = s_floor[tt];
-                const float x = fmaxf(db10(fmaxf(a.amin, row[n])) - ref_db, floor_db);
-                if (a.dct_fold) {
-                    const int n2 = N - 1 - n;
-                    if (n2 != n) {
-                        const float y = fmaxf(db10(fmaxf(a.amin, row[n2])) - ref_db, floor_db);
-                        se[tt * ld + n] = (double)x + (double)y;
-                        so[tt * ld + n] = (double)x - (double)y;
-                    } else {
-                        se[tt * ld + n] = (double)x;
-                        so[tt * ld + n] = 0.0;
+            // S_db tile: the chunk's raw mel energies of these frames are ONE contiguous block of nt * N floats -> coalesced 16-byte
+            // loads, four in flight per thread before the first use (the kernel is bound by the latency of these loads), dB
+            // conversion with the frame's reference / clamp, FP32 tile in shared memory.
+            {
+                const float* const blk = a.melws + gf0 * N;             // 128 N bytes per full tile: 16-byte aligned
+                const int n_el = nt * N, n_ch = (n_el + 3) >> 2;
+                for (int c0 = tid; c0 < n_ch; c0 += 4 * kThreads) {
+                    float4 v[4];
+                    SYG_UNROLL
+                    for (int r = 0; r < 4; ++r) {
+                        const int c = c0 + r * kThreads, e = 4 * c;
+                        v[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (e + 3 < n_el) v[r] = __ldg(reinterpret_cast<const float4*>(blk) + c);
+                        else if (e < n_el) {
+                            v[r].x = __ldg(blk + e);
+                            if (e + 1 < n_el) v[r].y = __ldg(blk + e + 1);
+                            if (e + 2 < n_el) v[r].z = __ldg(blk + e + 2);
+                        }
                     }
-                } else {
-                    se[tt * ld + n] = (double)x;
+                    SYG_UNROLL
+                    for (int r = 0; r < 4; ++r) {
+                        const int e = 4 * (c0 + r * kThreads);
+                        if (e >= n_el) break;
+                        int tt = e / N, n = e - tt * N;
+                        const float in[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+                        if (n + 3 < N && e + 3 < n_el) {                // chunk inside one row (always, when N is a multiple of 4)
+                            const float ref_db = s_ref[tt], floor_db = s_floor[tt];
+                            float4 o;
+                            o.x = fmaxf(db10(fmaxf(a.amin, in[0])) - ref_db, floor_db);
+                            o.y = fmaxf(db10(fmaxf(a.amin, in[1])) - ref_db, floor_db);
+                            o.z = fmaxf(db10(fmaxf(a.amin, in[2])) - ref_db, floor_db);
+                            o.w = fmaxf(db10(fmaxf(a.amin, in[3])) - ref_db, floor_db);
+                            if ((n & 3) == 0) *reinterpret_cast<float4*>(xs + tt * P + n) = o;
+                            else { xs[tt * P + n] = o.x; xs[tt * P + n + 1] = o.y; xs[tt * P + n + 2] = o.z; xs[tt * P + n + 3] = o.w; }
+                        } else {
+                            for (int q = 0; q < 4 && e + q < n_el; ++q) {
+                                xs[tt * P + n] = fmaxf(db10(fmaxf(a.amin, in[q])) - s_ref[tt], s_floor[tt]);
+                                if (++n == N) { n = 0; ++tt; }
+                            }
+                        }
+                    }
                 }
             }
             __syncthreads();
-            // work item = (frame, pair of coefficients of equal parity): the pair shares every load of the folded tile
-            const int n_ev = (a.n_mfcc + 1) / 2, n_od = a.n_mfcc / 2;
-            const int it_ev = (n_ev + 1) / 2, it_od = (n_od + 1) / 2;
-            for (int i = tid; i < (it_ev + it_od) * kFinTT; i += kThreads) {
-                const int item = i / kFinTT, tt = i - item * kFinTT;
-                if (tt >= nt) continue;
-                const bool odd = item >= it_ev;
-                const int c0 = odd ? 1 + 4 * (item - it_ev) : 4 * item;
-                const int c1 = c0 + 2;
-                const bool two = c1 < a.n_mfcc;
-                const double* d0 = a.dct + (long long)c0 * N;
-                const double* d1 = a.dct + (long long)(two ? c1 : c0) * N;
-                const double* s = (odd ? so : se) + tt * ld;
-                double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;              // two chains per coefficient (DFMA latency)
-                int n = 0;
-                for (; n + 2 <= H; n += 2) {
-                    const double s0 = s[n], s1 = s[n + 1];
-                    p0 = fma(__ldg(&d0[n]), s0, p0);
-                    q0 = fma(__ldg(&d1[n]), s0, q0);
-                    p1 = fma(__ldg(&d0[n + 1]), s1, p1);
-                    q1 = fma(__ldg(&d1[n + 1]), s1, q1);
+            // DCT as FP64 tensor-core products (mma.sync m8n8k4, DMMA): D[coefficient][frame] += dct[coefficient][n] * S[frame][n].
+            // Warp w owns one parity (even coefficients see the folded sums, odd ones the differences: see the B fragment below) and one
+            // n-tile of 8 frames; 8 coefficients of that parity per m-tile.  Per k-step of 4 mel columns a lane loads ONE table
+            // entry and ONE tile entry for 256 multiply-adds of the warp (the scalar version needed 1.5 loads per FMA and was
+            // bound by the load/store unit: 3.5 ms per 10 h of audio).
+            {
+                const int par = warp & 1, nt8 = (warp >> 1) * 8;       // kThreads / 32 = 8 warps: 2 parities x 4 n-tiles of 8 frames
+                const int g = lane >> 2, q = lane & 3;
+                const int n_par = par ? a.n_mfcc / 2 : (a.n_mfcc + 1) / 2;
+                const float* const xrow = xs + (nt8 + g) * P;            // this lane's frame (B column)
+                const double sgn = par ? -1.0 : 1.0;
+                for (int m0 = 0; m0 < n_par; m0 += 8) {
+                    const int c_a = par + 2 * (m0 + g);                 // coefficient of this lane's A row
+                    const bool a_ok = c_a < a.n_mfcc;
+                    const double* const drow = a.dct + (long long)(a_ok ? c_a : 0) * N + q;
+                    double d0 = 0.0, d1 = 0.0;
+                    for (int k0 = 0; k0 < H4; k0 += 4) {
+                        const int k = k0 + q;
+                        const double av = (a_ok && k < H) ? __ldg(drow + k0) : 0.0;
+                        // DCT-II rows are (-1)^c symmetric about the centre (cos(pi c (2(N-1-n)+1) / 2N) = (-1)^c cos(pi c (2n+1) / 2N)):
+                        // even coefficients see s[n] + s[N-1-n], odd ones s[n] - s[N-1-n], n < ceil(N/2) (centre of an odd N once);
+                        // folded here, in FP64, on the way into the fragment.  Other DCT types read the unfolded row.
+                        double bv = 0.0;
+                        if (k < H) {
+                            bv = (double)xrow[k];
+                            if (a.dct_fold) {
+                                const int k2 = N - 1 - k;
+                                bv = (k2 != k) ? bv + sgn * (double)xrow[k2] : (par ? 0.0 : bv);
+                            }
+                        }
+                        mma_m8n8k4_f64(d0, d1, av, bv);
+                    }
+                    // lane holds D[row g][cols 2q, 2q+1] = coefficient par + 2 (m0 + g) of frames nt8 + 2q, nt8 + 2q + 1
+                    if (a_ok) {
+                        const int t0 = nt8 + 2 * q;
+                        if (t0 < nt) a.out[s_out[t0] + (long long)(a.row_mfcc + c_a) * a.T] = (float)d0;
+                        if (t0 + 1 < nt) a.out[s_out[t0 + 1] + (long long)(a.row_mfcc + c_a) * a.T] = (float)d1;
+                    }
                 }
-                if (n < H) {
-                    p0 = fma(__ldg(&d0[n]), s[n], p0);
-                    q0 = fma(__ldg(&d1[n]), s[n], q0);
-                }
-                float* const o = a.out + s_out[tt];
-                o[(long long)(a.row_mfcc + c0) * a.T] = (float)(p0 + p1);
-                if (two) o[(long long)(a.row_mfcc + c1) * a.T] = (float)(q0 + q1);
             }
         }
         if (a.nb > 0) {

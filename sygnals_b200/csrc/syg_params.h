@@ -8,6 +8,12 @@ constexpr int kThreads = 256;               // threads per CTA of every kernel
 constexpr int MODE_FEATURES = 0;            // frame kernel modes
 constexpr int MODE_STFT = 1;
 constexpr int kFinTT = 32;                  // frames per finalize CTA
+// row pitch (floats) of the finalize kernel's S_db tile for N mel bands: >= N and 4 mod 8, so that rows start 16-byte aligned
+// and the 8 frames x 4 columns of a DMMA B fragment (and its mirrored columns) fall on 32 distinct banks
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int fin_pitch(int N) { int p = (N + 3) / 4 * 4; while ((p & 7) != 4) p += 4; return p; }
 }  // namespace sygdev
 
 namespace syg {

@@ -188,6 +188,8 @@ def test_golden_cfg5_welch(eng):
     (16000, 64, 16, 700, ["mfcc", "spectral_centroid"], {"mfcc": {"n_mels": 10, "n_mfcc": 5}}),
     (16000, 32, 8, 300, ["spectral_centroid", "spectral_rolloff", "rms_energy"], None),
     (16000, 128, 32, 1000, ["mfcc", "crest_factor"], {"mfcc": {"n_mels": 16, "dct_type": 3}}),
+    (22050, 512, 128, 4100, ["mfcc"], {"mfcc": {"n_mels": 23, "n_mfcc": 23}}),                  # odd n_mels (fold centre term), two DMMA m-tiles per parity
+    (22050, 1024, 256, 5000, ["mfcc"], {"mfcc": {"n_mels": 46, "n_mfcc": 40, "dct_type": 3}}),  # unfolded tile, three m-tiles
     (48000, 4096, 1024, 20000, ["mfcc", "spectral_centroid", "rms_energy"], None),
     (48000, 8192, 2048, 30000, ["mfcc", "spectral_rolloff", "crest_factor"], None),
 ])
