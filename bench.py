@@ -36,6 +36,28 @@ WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries write banners straight to file descriptor 1 (NCCL prints its version
+    there whenever NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the JSON goes out through a saved copy."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -109,7 +131,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     return 0
 
 
@@ -173,8 +195,6 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO in the box environment) off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("SYGB200_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
     sr, fl, hop = w["sr"], w["fl"], w["hop"]
@@ -340,7 +360,7 @@ def run_native(args):
                 line["cpu_baseline"] = ref["cpu_baseline"]
             except Exception as exc:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": None, "kind": "port", "sample": f"failed: {exc}"}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -360,6 +380,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-units", type=int, default=0, help="segments per step of the CPU reference arm")
     args = ap.parse_args()
+    guard_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_native(args)
