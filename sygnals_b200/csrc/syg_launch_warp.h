@@ -42,18 +42,21 @@ static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, 
 template <bool EXTRA, int STAGE>
 static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using namespace sygdev;
-    constexpr int MINB = 2;
+    constexpr int MINB = 2, NT = 256;
+    // STFT stage: the CTA tile couples the warps of a CTA through two barriers per round; 4-warp CTAs (4 per SM) measured
+    // 8 % / 5 % faster than 8-warp ones for n_fft 256 / 1024, equal for 512, 15 % slower for 2048 (cfg2, B200)
+    constexpr int NT3 = (STAGE == 3) ? 128 : NT, MINB3 = (STAGE == 3) ? 4 : MINB;
     switch (ilog2i(n_fft / 2)) {
-        case 4: return frame_warp_t<FftTile<4, 4>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
-        case 5: return frame_warp_t<FftTile<5, 8>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
-        case 6: return frame_warp_t<FftTile<6, 8>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
-        case 7: return frame_warp_t<FftTile<7, 16>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
-        case 8: return frame_warp_t<FftTile<8, 16>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
-        case 9: return frame_warp_t<FftTile<9, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+        case 4: return frame_warp_t<FftTile<4, 4>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
+        case 5: return frame_warp_t<FftTile<5, 8>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
+        case 6: return frame_warp_t<FftTile<6, 8>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
+        case 7: return frame_warp_t<FftTile<7, 16>, EXTRA, NT3, MINB3, STAGE>(a, sm_count, st, err);
+        case 8: return frame_warp_t<FftTile<8, 16>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
+        case 9: return frame_warp_t<FftTile<9, 32>, EXTRA, NT3, MINB3, STAGE>(a, sm_count, st, err);
         case 10:
             // features: one CTA of 16 warps per SM so that the 38 KB of plan tables are held once (leaves ~50 KB of L1)
             if (STAGE == 0) return frame_warp_t<FftTile<10, 32>, EXTRA, 512, 1, STAGE>(a, sm_count, st, err);
-            return frame_warp_t<FftTile<10, 32>, EXTRA, 256, MINB, STAGE>(a, sm_count, st, err);
+            return frame_warp_t<FftTile<10, 32>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
     }
     err = "n_fft=" + std::to_string(n_fft) + " has no warp tile";
     return -5;
