@@ -50,6 +50,11 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
         const float* yb = a.y + ur.start;
         for (int i = lane; i < FW * PS; i += 32) accw[i] = 0.0f;
         __syncwarp();
+        // unit rms / crest / peak ride on the sub-segment loads: sub-segment s accounts for its first `step` samples (the rest
+        // belongs to its successors), the last one for all of its nperseg samples; samples behind the last sub-segment are
+        // swept afterwards.  Every sample of the unit is counted exactly once and read from memory for the FFT only.
+        double sqd = 0.0;
+        float pk = 0.0f;
         for (int s0 = 0; s0 < a.nseg; s0 += FW) {
             const int s = s0 + f;
             const bool valid = s < a.nseg;
@@ -77,6 +82,25 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                     z[r] = v;
                     if (r & 1) sm23 = __fadd2_rn(sm23, v); else sm01 = __fadd2_rn(sm01, v);
                 }
+            }
+            if (a.stats && valid) {
+                const int lim = (s == a.nseg - 1) ? a.nperseg : a.step;
+                float2 sq = make_float2(0.0f, 0.0f);
+                float pk2 = 0.0f;
+                SYG_UNROLL
+                for (int r = 0; r < E; ++r) {
+                    const int c2 = 2 * (j + r * G);
+                    if (c2 + 1 < lim) {
+                        sq = __ffma2_rn(z[r], z[r], sq);
+                        pk = fmaxf(pk, fabsf(z[r].x));
+                        pk2 = fmaxf(pk2, fabsf(z[r].y));
+                    } else if (c2 < lim) {
+                        sq.x = __fmaf_rn(z[r].x, z[r].x, sq.x);
+                        pk = fmaxf(pk, fabsf(z[r].x));
+                    }
+                }
+                pk = fmaxf(pk, pk2);
+                sqd += (double)(sq.x + sq.y);                          // float32 partial sums of <= 2 E terms, float64 across
             }
             float mean = 0.0f;
             if (a.detrend) {                                          // scipy detrend('constant'): subtract the sub-segment mean
@@ -159,30 +183,9 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
         }
         if (a.stats) {                                                // rms / crest / peak of the whole unit
             float2 sq = make_float2(0.0f, 0.0f);
-            double sqd = 0.0;
-            float pk = 0.0f;
-            long long i = 0;
-            if (ur.valid >= a.g.unit_len && (reinterpret_cast<uintptr_t>(yb) & 15u) == 0) {       // whole unit present, 16-byte aligned
-                const float4* y4 = reinterpret_cast<const float4*>(yb);
-                const long long n4 = a.g.unit_len >> 2;
-                int run = 0;
-                float2 sq2 = make_float2(0.0f, 0.0f);
-                for (long long q = lane; q < n4; q += 32) {
-                    const float4 v = __ldg(y4 + q);
-                    sq = __ffma2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y), sq);
-                    sq2 = __ffma2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w), sq2);
-                    pk = fmaxf(pk, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-                    if (++run == 16) {                                 // float32 partial sums of 64 terms, float64 across
-                        sqd += (double)((sq.x + sq.y) + (sq2.x + sq2.y));
-                        sq = make_float2(0.0f, 0.0f); sq2 = sq; run = 0;
-                    }
-                }
-                sqd += (double)((sq.x + sq.y) + (sq2.x + sq2.y));
-                sq = make_float2(0.0f, 0.0f);
-                i = n4 << 2;
-            }
             int run = 0;
-            for (i += lane; i < a.g.unit_len; i += 32) {
+            const long long covered = a.nseg > 0 ? (long long)(a.nseg - 1) * a.step + a.nperseg : 0;
+            for (long long i = covered + lane; i < a.g.unit_len; i += 32) {
                 const float v = (i < ur.valid) ? __ldg(yb + i) : 0.0f;
                 sq.x = __fmaf_rn(v, v, sq.x);
                 pk = fmaxf(pk, fabsf(v));
