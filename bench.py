@@ -194,6 +194,10 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host placement for the end-to-end arm: this rank's pinned buffers live on its GPU's NUMA node (no effect on `value`)
+    from sygnals_b200.utils import numa
+    full_affinity = os.sched_getaffinity(0)
+    placement = None if os.environ.get("SYGB200_NO_NUMA_BIND") else numa.bind_to_device_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
@@ -273,7 +277,7 @@ def run_native(args):
         same = bool(torch.equal(oh.to(dev), out))
         e2e = {"value": world * audio_s * ne / dt, "unit": "audio-s/s", "h2d_bytes_per_step": int(total * 4),
                "d2h_bytes_per_step": int(out.numel() * 4), "steps": ne, "ms_per_step": 1e3 * dt / ne,
-               "matches_device_path": same}
+               "matches_device_path": same, "host_placement": placement}
         del yh
         # additive ingest path: the same recording as 16-bit PCM (what the WAV files hold); the float32 line
         # above stays the headline because it is the reference's own in-memory format
@@ -294,6 +298,7 @@ def run_native(args):
         e2e["pcm16"] = {"value": world * audio_s * ne / dt16, "unit": "audio-s/s", "h2d_bytes_per_step": int(total * 2),
                         "d2h_bytes_per_step": int(out.numel() * 4), "ms_per_step": 1e3 * dt16 / ne}
         del y16, oh
+    os.sched_setaffinity(0, full_affinity)                 # the CPU baseline below uses every host core again
 
     gather_ms = None
     if world > 1:
