@@ -70,3 +70,14 @@ def test_plan_tables_match_oracle_shim():
     np.testing.assert_allclose(lib.debug_dct(13, 40), scipy.fftpack.dct(np.eye(40), type=2, norm="ortho", axis=0)[:13], atol=1e-7)
     import scipy.signal
     np.testing.assert_allclose(lib.debug_window(0, 2048, 2048), scipy.signal.get_window("hann", 2048, fftbins=True), atol=1e-7)
+
+
+def test_numa_helper_is_a_noop_without_a_gpu():
+    from sygnals_b200.utils import numa
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set()
+    import os
+    before = os.sched_getaffinity(0)
+    r = numa.bind_to_device_node(0)
+    assert r is None or set(os.sched_getaffinity(0)) <= set(before)
+    os.sched_setaffinity(0, before)
