@@ -46,6 +46,8 @@ _REBIND_TARGETS: List[Tuple[str, str, Tuple[str, ...]]] = [
     ("sygnals.core.dsp", "compute_psd_welch", ("sygnals.core",)),
     ("sygnals.core.dsp", "compute_psd_periodogram", ("sygnals.core",)),
     ("sygnals.core.segmentation", "segment_fixed_length", ("sygnals.cli.segment_cmd",)),
+    ("sygnals.core.audio.features", "rms_energy", ()),
+    ("sygnals.core.audio.features", "zero_crossing_rate", ()),
 ]
 
 
@@ -166,6 +168,28 @@ class SygnalsB200Plugin(SygnalsPluginBase):
         segment_fixed_length.__wrapped_reference__ = original
         return segment_fixed_length
 
+    def _make_audio_feature(self, which: str, original: Optional[Callable]) -> Callable:
+        from .core.audio import features as af
+        mirror = getattr(af, which)
+
+        def feature(y=None, *args, **kw):
+            fl = args[0] if args else kw.get("frame_length", 2048)
+            reason = None
+            if not _pow2_in_range(fl):
+                reason = f"frame_length={fl} is not a power of two in [32, 8192]"
+            elif kw.get("S") is not None:
+                reason = "spectrogram input has no CUDA kernel"
+            elif kw.get("pad_mode", "constant") != "constant":
+                reason = f"pad_mode={kw.get('pad_mode')!r} is not built into the engine"
+            elif set(kw) - {"S", "frame_length", "hop_length", "center", "pad_mode"}:
+                reason = "extra librosa keyword arguments"
+            fn = self._engine_ok(which, reason, original) or mirror
+            return fn(y, *args, **kw)
+
+        feature.__name__ = which
+        feature.__wrapped_reference__ = original
+        return feature
+
     def _replacement(self, attr: str, original: Optional[Callable]) -> Callable:
         if attr == "extract_features":
             return self.make_extract_features(original)
@@ -175,6 +199,8 @@ class SygnalsB200Plugin(SygnalsPluginBase):
             return self._make_psd(attr, original)
         if attr == "segment_fixed_length":
             return self.make_segment_fixed_length(original)
+        if attr in ("rms_energy", "zero_crossing_rate"):
+            return self._make_audio_feature(attr, original)
         raise KeyError(attr)
 
     # ------------------------------------------------------------------ rebinding

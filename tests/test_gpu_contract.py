@@ -176,6 +176,29 @@ def test_rms_energy_sine_and_silence(engine):
     assert_allclose(z, 0.0, atol=1e-7)
 
 
+def test_audio_features_module_mirror(engine):
+    """tests/test_audio_features.py:95-116 against the mirror of sygnals.core.audio.features (same names and signatures)."""
+    from sygnals_b200.core.audio.features import rms_energy, zero_crossing_rate
+    sr, freq, amp = 22050, 440.0, 0.7
+    t = np.linspace(0, 1.0, sr, endpoint=False)
+    sine = (amp * np.sin(2 * np.pi * freq * t)).astype(np.float64)
+    zcr = zero_crossing_rate(sine, frame_length=1024, hop_length=512)
+    assert zcr.ndim == 1 and zcr.dtype == np.float64 and np.all(zcr >= 0) and len(zcr) == 1 + sr // 512
+    assert abs(np.mean(zcr) - 2 * freq / sr) < 0.05
+    assert_allclose(zero_crossing_rate(np.zeros(sr), frame_length=1024, hop_length=512), 0.0, atol=1e-7)
+    assert np.mean(zero_crossing_rate(np.random.default_rng(0).standard_normal(sr), frame_length=1024, hop_length=512)) > 0.1
+    rms = rms_energy(y=sine, frame_length=1024, hop_length=512)
+    assert rms.ndim == 1 and rms.dtype == np.float64 and np.all(rms >= 0)
+    assert_allclose(np.mean(rms), amp / np.sqrt(2), atol=0.05)
+    assert_allclose(rms_energy(y=np.zeros(sr), frame_length=1024, hop_length=512), 0.0, atol=1e-7)
+    with pytest.raises(ValueError):
+        rms_energy()
+    with pytest.raises(ValueError):
+        rms_energy(y=np.zeros((2, 100)))
+    with pytest.raises(NotImplementedError):
+        rms_energy(S=np.ones((5, 4)))
+
+
 # ------------------------------------------------------------------------------------------------ dsp
 def test_compute_stft(engine):
     fs, freq = 1000.0, 50.0

@@ -68,6 +68,14 @@ def test_reference_loader_accepts_the_plugin_and_rebinding_round_trips():
         np.testing.assert_array_equal(a["zero_crossing_rate"], b["zero_crossing_rate"])
         a = dsp.compute_stft(y, n_fft=300)                      # non power of two -> reference
         np.testing.assert_array_equal(a, orig[2](y, n_fft=300))
+        # array-level audio features: rebound, unsupported geometry routed to the ORIGINAL (bit-identical)
+        import sygnals.core.audio.features as af
+        assert getattr(af.rms_energy, "__wrapped_reference__", None) is not None
+        r_a = af.rms_energy(y=y, frame_length=500, hop_length=125)
+        r_b = af.rms_energy.__wrapped_reference__(y=y, frame_length=500, hop_length=125)
+        np.testing.assert_array_equal(r_a, r_b)
+        z_a = af.zero_crossing_rate(y, frame_length=500, hop_length=125)
+        np.testing.assert_array_equal(z_a, af.zero_crossing_rate.__wrapped_reference__(y, frame_length=500, hop_length=125))
         # error contract unchanged (manager.py:141-143)
         with pytest.raises(ValueError, match="Unknown feature"):
             fc.extract_features(y, 22050, ["nope"])
@@ -77,6 +85,7 @@ def test_reference_loader_accepts_the_plugin_and_rebinding_round_trips():
         assert len(segs_a) == len(segs_b) and all(np.array_equal(p, q) for p, q in zip(segs_a, segs_b))
         inst.teardown()
         assert (mgr.extract_features, fc.extract_features, dsp.compute_stft, sc.segment_fixed_length) == orig
+        assert getattr(af.rms_energy, "__wrapped_reference__", None) is None
     finally:
         logging.disable(logging.NOTSET)
 
