@@ -78,6 +78,8 @@ SYG_DEVICE SYG_INLINE double lanes_scan_incl(double v, int gl) {
 
 // STAGE 0: features (framing -> FFT -> |X|^2 in shared memory -> all epilogues).
 // STAGE 3: STFT output (framing -> FFT -> real split -> transposed CTA tile -> contiguous row stores).
+// STAGE 4: STFT magnitude / power output for M <= 256 (n_fft <= 512): every WARP owns 8 consecutive frames and a private transposed
+//          tile [B][8 + 1] -- no CTA barrier at all, the warps of an SM drift apart and overlap each other's load / FFT / store phases.
 // (A two-launch variant -- FFT kernel + 64-register epilogue kernel with the spectra handed over through a workspace -- was
 // measured and removed: +4 % at best, see DESIGN.md 4.1 and profiles/r01_t_two_stage_ncu_summary.txt.  CTA barriers between
 // the phases of the fused kernel were measured too: +8 % time.)
@@ -98,6 +100,12 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     constexpr int TT = WT::kWarps * FW, TTP = TT + 1;
     long long* const slot_off = reinterpret_cast<long long*>(reinterpret_cast<float*>(smem_raw) + WT::kWarps * WF);   // [TT]
     float* const tile = reinterpret_cast<float*>(slot_off + TT);                                                    // [B][TTP] float or float2
+    // STAGE 4: per-warp block behind the warps' regions: 8 output offsets (long long) + tile [B][9] floats
+    constexpr int TT4 = 8, TTP4 = TT4 + 1, SUBS = (STAGE == 4) ? TT4 / FW : 1;
+    constexpr int WB4 = 2 * TT4 + ((B * TTP4 + 1) & ~1);               // floats per warp block (even: keeps the offsets 8-byte aligned)
+    float* const wblk = reinterpret_cast<float*>(smem_raw) + WT::kWarps * WF + warp * WB4;
+    long long* const woff = reinterpret_cast<long long*>(wblk);       // [TT4]
+    float* const wtile = wblk + 2 * TT4;                              // [B][TTP4]
     float* const pww = wbase;                                         // [FW][RSS]  Z (float2, zpad layout), later |X|^2 (ppad layout)
     float2* const zs = reinterpret_cast<float2*>(wbase + f * RSS);
     float* const pf = wbase + f * RSS;
@@ -137,23 +145,33 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     const long long n_tasks = (a.n_frames + FW - 1) / FW;
     // (unit, frame-in-unit) of this lane's frame advance incrementally: one division per kernel instead of one per frame
     const long long stride_tasks = (long long)gridDim.x * WT::kWarps;
-    const long long stride_frames = stride_tasks * FW;
+    // STAGE 4 walks "super tasks" of 8 consecutive frames (SUBS tasks each) per warp: small steps of FW frames inside one, a
+    // large step to the warp's next super task
+    const long long stride_frames = (STAGE == 4) ? (stride_tasks - 1) * TT4 + FW : stride_tasks * FW;
     const long long du = stride_frames / a.T;
     const int dt = (int)(stride_frames - du * a.T);
-    long long gf_run = ((long long)blockIdx.x * WT::kWarps + warp) * FW + f;
+    long long gf_run = ((long long)blockIdx.x * WT::kWarps + warp) * ((STAGE == 4) ? TT4 : FW) + f;
     long long u_run = gf_run / a.T;
     int t_run = (int)(gf_run - u_run * a.T);
-    // all warps of the CTA run the same number of iterations (tasks past the end are processed as empty frames)
-    for (long long task0 = (long long)blockIdx.x * WT::kWarps; task0 < n_tasks; task0 += stride_tasks) {
-        const long long task = task0 + warp;
+    const long long task_begin = (STAGE == 4) ? ((long long)blockIdx.x * WT::kWarps + warp) * SUBS : (long long)blockIdx.x * WT::kWarps;
+    const long long task_end = (STAGE == 4) ? ((a.n_frames + TT4 - 1) / TT4) * SUBS : n_tasks;
+    // STAGE 0 / 3: all warps of the CTA run the same number of iterations (tasks past the end are processed as empty frames)
+    for (long long task0 = task_begin; task0 < task_end;
+         task0 = (STAGE == 4) ? ((((task0 + 1) & (SUBS - 1)) != 0) ? task0 + 1 : task0 + 1 + (stride_tasks - 1) * SUBS) : task0 + stride_tasks) {
+        const long long task = (STAGE == 4) ? task0 : task0 + warp;
         const long long gf = gf_run;
         const bool valid = gf < a.n_frames;
         const long long u = valid ? u_run : 0;
         const int t = valid ? t_run : 0;
-        gf_run += stride_frames;
-        u_run += du;
-        t_run += dt;
-        if (t_run >= a.T) { t_run -= a.T; ++u_run; }
+        if (STAGE == 4 && ((task0 + 1) & (SUBS - 1)) != 0) {          // next task of the same super task: FW frames on
+            gf_run += FW;
+            t_run += FW;
+        } else {
+            gf_run += stride_frames;
+            u_run += du;
+            t_run += dt;
+        }
+        while (t_run >= a.T) { t_run -= a.T; ++u_run; }
         UnitRef ur = unit_ref(a.g, u);
         if (!valid) ur.valid = 0;
         const long long p0 = (long long)t * a.hop - a.cpad;
@@ -285,6 +303,18 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 const int kk = i * G;
                 const int k = j + kk;
                 if (i == E / 2 && j != 0) break;
+                if (STAGE == 4) {
+                    const float2 w = __ldg(&a.tws[k]);
+                    float xkr, xki, xmr, xmi;
+                    real_split(zk[i].x, zk[i].y, zm[i].x, zm[i].y, w.x, w.y, xkr, xki, xmr, xmi);
+                    const int slot = (int)(task & (SUBS - 1)) * FW + f;
+                    const int k2 = M - k;
+                    float pk_ = __fmaf_rn(xkr, xkr, xki * xki), pm_ = __fmaf_rn(xmr, xmr, xmi * xmi);
+                    if (a.out_kind == 1) { pk_ = sqrt_approx(pk_); pm_ = sqrt_approx(pm_); }
+                    wtile[k * TTP4 + slot] = pk_;
+                    if (k2 != k) wtile[k2 * TTP4 + slot] = pm_;
+                    continue;
+                }
                 if (STAGE == 3) {
                     const float2 w = __ldg(&a.tws[k]);
                     float xkr, xki, xmr, xmi;
@@ -315,6 +345,23 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         __syncwarp();
 
 
+        if (STAGE == 4) {
+            // ---------------- STFT output, warp-private: after the super task's last frames, rows of 8 frames per bin ----------------
+            if (j == 0) woff[(int)(task & (SUBS - 1)) * FW + f] = valid ? ((long long)u * B) * a.T + t : -1;
+            __syncwarp();
+            if (((task0 + 1) & (SUBS - 1)) == 0) {
+                const int sl = lane & (TT4 - 1), kq = lane / TT4;       // 4 rows of 8 frames per warp instruction
+                const long long off = woff[sl];
+                if (off >= 0) {
+                    const float* src = wtile + kq * TTP4 + sl;
+                    float* dst = reinterpret_cast<float*>(a.stft_out) + off + (long long)kq * a.T;
+                    const long long dstep = 4LL * a.T;
+                    for (int k = kq; k < B; k += 4, src += 4 * TTP4, dst += dstep) *dst = *src;
+                }
+                __syncwarp();                                           // the tile is refilled by the warp's next super task
+            }
+            continue;
+        }
         if (STAGE == 3) {
             // ---------------- STFT output: rows of TT consecutive frames per bin leave the CTA as contiguous runs ----------------
             if (j == 0) slot_off[warp * FW + f] = valid ? ((long long)u * B) * a.T + t : -1;

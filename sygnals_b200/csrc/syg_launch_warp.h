@@ -8,7 +8,7 @@
 
 namespace syglaunch {
 
-// STAGE 0: features; 3: STFT output (see syg_frame_warp.cuh)
+// STAGE 0: features; 3: STFT output through a CTA tile; 4: STFT magnitude / power through warp-private tiles (see syg_frame_warp.cuh)
 template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using WT = sygdev::WarpTile<TL, NT>;
@@ -22,6 +22,7 @@ static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, 
         const int TT = WT::kWarps * WT::FW;
         smem += (size_t)TT * sizeof(long long) + (size_t)(WT::M + 1) * (TT + 1) * (wide ? 8 : 4);
     }
+    if (STAGE == 4) smem += (size_t)WT::kWarps * (16 + (((WT::M + 1) * 9 + 1) & ~1)) * sizeof(float);   // per warp: 8 offsets + tile [B][9]
     if (blocks_per_sm[wide] == 0 || smem > smem_seen[wide]) {
         smem_seen[wide] = smem;
         LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + (STAGE == 3 && !wide ? (WT::M + 1) * (WT::kWarps * WT::FW + 1) * 4 : 0)));
@@ -30,7 +31,7 @@ static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, 
         if (nb < 1) { err = "frame_warp kernel does not fit on an SM"; return -3; }
         blocks_per_sm[wide] = nb;
     }
-    const long long per_cta = (long long)WT::FW * WT::kWarps;
+    const long long per_cta = (long long)((STAGE == 4) ? 8 : WT::FW) * WT::kWarps;
     const long long n_rounds = (a.n_frames + per_cta - 1) / per_cta;
     if (n_rounds <= 0) return 0;
     const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm[wide]);
