@@ -53,8 +53,11 @@ static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count,
         case 6: return frame_warp_t<FftTile<6, 8>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
         case 7: return frame_warp_t<FftTile<7, 16>, EXTRA, NT3, MINB3, STAGE>(a, sm_count, st, err);
         case 8: return frame_warp_t<FftTile<8, 16>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
-        case 9: return frame_warp_t<FftTile<9, 32>, EXTRA, NT3, MINB3, STAGE>(a, sm_count, st, err);
+        case 9:
+            if constexpr (STAGE == 4) break;                          // warp-private tiles exist for M <= 256 only
+            else return frame_warp_t<FftTile<9, 32>, EXTRA, NT3, MINB3, STAGE>(a, sm_count, st, err);
         case 10:
+            if constexpr (STAGE == 4) break;
             // features: one CTA of 16 warps per SM so that the 38 KB of plan tables are held once (leaves ~50 KB of L1)
             if (STAGE == 0) return frame_warp_t<FftTile<10, 32>, EXTRA, 512, 1, STAGE>(a, sm_count, st, err);
             return frame_warp_t<FftTile<10, 32>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
