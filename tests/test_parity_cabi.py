@@ -123,6 +123,23 @@ def test_golden_cfg2_stft(eng, n_fft):
         power_close(mag[c].astype(np.float64) ** 2, np.abs(ref) ** 2)
 
 
+@pytest.mark.parametrize("n_fft,hop,n,L", [(32, 8, 5, 300), (64, 16, 7, 1000), (128, 32, 3, 777), (256, 64, 9, 1601), (512, 128, 11, 3000),
+                                           (512, 100, 4, 1234), (1024, 256, 3, 5000)])
+def test_stft_real_outputs_ragged_batches_vs_oracle(eng, n_fft, hop, n, L):
+    """Magnitude / power output of the small transforms (warp-private tiles of 8 consecutive frames, n_fft <= 512): clip counts and
+    frame counts that are not multiples of 8, so tiles straddle clips and the last one is partial."""
+    rng = np.random.default_rng(n_fft + L)
+    y = rng.standard_normal((n, L)).astype(np.float32)
+    u = eng.units_clips(n, L)
+    mag = eng.stft_host(y.ravel(), u, n_fft, hop, n_fft, out_kind=_ffi.OUT_MAGNITUDE)
+    pw = eng.stft_host(y.ravel(), u, n_fft, hop, n_fft, out_kind=_ffi.OUT_POWER)
+    for c in range(n):
+        ref = np.abs(orc.compute_stft(y[c].astype(np.float64), n_fft=n_fft, hop_length=hop)) ** 2
+        assert mag[c].shape == pw[c].shape == ref.shape == (1 + n_fft // 2, 1 + L // hop)
+        power_close(pw[c].astype(np.float64), ref)
+        power_close(mag[c].astype(np.float64) ** 2, ref)
+
+
 def test_golden_cfg2_reflect_and_nocenter(eng):
     y, sr = cases.cfg2_input()
     g = cases.load("cfg2_stft_sweep.npz")
