@@ -561,12 +561,22 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 float acc = 0.0f;
                 if (a.mel_power_is_2) {
                     float2 m01 = make_float2(0.0f, 0.0f), m23 = m01;
+                    int i = 0;
 #ifndef SYG_EMU
 #pragma unroll 1
 #endif
-                    for (int i = 0; i < d.z; i += 4) {                  // steps come in multiples of four (syg_plan.h)
+                    for (; i + 4 <= d.z; i += 4) {                      // steps come in multiples of two (syg_plan.h): fours, then a tail of two
                         SYG_UNROLL
                         for (int c = 0; c < 4; ++c) {
+                            const float4 w = TBL ? wv[GS * (i + c)] : __ldg(wv + GS * (i + c));
+                            const float4 q = pp4[i + c];
+                            m01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(q.x, q.y), m01);
+                            m23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(q.z, q.w), m23);
+                        }
+                    }
+                    if (i < d.z) {
+                        SYG_UNROLL
+                        for (int c = 0; c < 2; ++c) {
                             const float4 w = TBL ? wv[GS * (i + c)] : __ldg(wv + GS * (i + c));
                             const float4 q = pp4[i + c];
                             m01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(q.x, q.y), m01);

@@ -182,7 +182,7 @@ inline void build_mel_slots(const MelTable& t, MelSlots& s, int n_bins, int gs) 
                 L = std::max(L, len[q0 + j]);
             }
         }
-        L = (L + 3) / 4 * 4;                                      // the kernel sweeps four steps per iteration
+        L = (L + 1) / 2 * 2;                                      // the kernel sweeps four steps per iteration plus an optional tail of two
         for (int j = 0; j < gn; ++j) {                              // keep the sweep inside the buffer, and the bank residue with it
             const int limit = ps_words - 4 * L;
             if (pst[j] > limit) {
