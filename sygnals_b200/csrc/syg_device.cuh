@@ -586,7 +586,22 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
         r.y = sqrt_approx(__uint_as_float(__reduce_min_sync(kFull, mn)));
         return r;
     }
-    const Sel4 t = track4(q, mine, count);
+    Sel4 t;
+    if (count <= 128) {
+        // every lane owns at most four elements: two 5-exchange sorts give both sorted quadruples directly (missing elements are
+        // 0 for the largest-first list and all-ones for the smallest-first list), no insertion loop
+        const bool h0 = lane < count, h1 = lane + 32 < count, h2 = lane + 64 < count, h3 = lane + 96 < count;
+        const unsigned e0 = h0 ? __float_as_uint(q[0]) : 0u, e1 = h1 ? __float_as_uint(q[36]) : 0u;
+        const unsigned e2 = h2 ? __float_as_uint(q[72]) : 0u, e3 = h3 ? __float_as_uint(q[108]) : 0u;
+        unsigned s0 = e0, s1 = e1, s2 = e2, s3 = e3;
+        cex(s0, s1); cex(s2, s3); cex(s0, s2); cex(s1, s3); cex(s1, s2);          // ascending
+        t.a0 = s3; t.a1 = s2; t.a2 = s1; t.a3 = s0;
+        unsigned r0 = h0 ? e0 : 0xffffffffu, r1 = h1 ? e1 : 0xffffffffu, r2 = h2 ? e2 : 0xffffffffu, r3 = h3 ? e3 : 0xffffffffu;
+        cex(r0, r1); cex(r2, r3); cex(r0, r2); cex(r1, r3); cex(r1, r2);
+        t.b0 = r0; t.b1 = r1; t.b2 = r2; t.b3 = r3;
+    } else {
+        t = track4(q, mine, count);
+    }
     // both directions as "largest key first": top keys = bits, bottom keys = ~bits (0 = nothing)
     unsigned a0 = t.a0, a1 = t.a1, a2 = t.a2, a3 = t.a3;
     unsigned b0 = ~t.b0, b1 = ~t.b1, b2 = ~t.b2, b3 = ~t.b3;
