@@ -36,7 +36,10 @@ struct WarpTile {
     static constexpr int kWarps = NT / 32;
     // one region per frame, used twice: as the Z exchange buffer of the FFT, then (Z is dead once the real split has pulled
     // its pairs into registers) as the |X|^2 spectrum.  Halves the shared memory per warp, which the SM hands to L1.
-    static constexpr int RS = ((2 * ZS > PS ? 2 * ZS : PS) + 3) / 4 * 4;
+    // With FW > 1 the lane groups of a warp store their |X|^2 in the same 32-bit shared-memory access: regions start G banks apart
+    // (pitch = G mod 32) so that the groups never collide.
+    static constexpr int RS0 = ((2 * ZS > PS ? 2 * ZS : PS) + 3) / 4 * 4;
+    static constexpr int RS = (FW == 1) ? RS0 : ((RS0 - G + 31) / 32 * 32 + G);
     static constexpr int warp_floats = FW * RS;
     static constexpr size_t bytes = (size_t)kWarps * warp_floats * sizeof(float);
     // plan tables kept in shared memory by the fused kernel (all 16-byte multiples): window [2M] floats, tw [M] float2,

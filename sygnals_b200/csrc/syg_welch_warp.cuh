@@ -19,7 +19,10 @@ namespace sygdev {
 template <class TL, int NT>
 struct WelchWarpTile {
     using WT = WarpTile<TL, NT>;
-    static constexpr int FW = WT::FW, ZS = WT::ZS, PS = WT::PS;
+    static constexpr int FW = WT::FW, ZS = WT::ZS;
+    // accumulator pitch: the FW lane groups of a warp add to their own accumulators in the same 32-bit shared-memory access, so the
+    // groups (G = 32 / FW lanes each) must start G banks apart: pitch = G (mod 32), at least WarpTile::PS
+    static constexpr int PS = (FW == 1) ? WT::PS : ((WT::PS - WT::G + 31) / 32 * 32 + WT::G);
     static constexpr int ZR = (2 * ZS + 3) / 4 * 4;                  // floats of one Z region
     static constexpr int warp_floats = FW * (ZR + PS);               // Z regions, then the accumulators
     static constexpr size_t bytes = (size_t)WT::kWarps * warp_floats * sizeof(float);
@@ -29,7 +32,7 @@ template <class TL, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchArgs a) {
     using WT = WarpTile<TL, NT>;
     using WW = WelchWarpTile<TL, NT>;
-    constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, PS = WT::PS, LE = WT::LOG2E;
+    constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, PS = WW::PS, LE = WT::LOG2E;
     constexpr int Q = E / R2;
     constexpr int B = M + 1;
     SYG_DYN_SMEM(smem_raw);
