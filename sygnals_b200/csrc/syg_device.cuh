@@ -614,7 +614,8 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
     // are exactly the largest elements of the band.  If there are at least n of them (the common case), the n pops never
     // leave the tracked quadruples and the lean loop needs no bookkeeping; otherwise (strongly clustered spectra) the
     // full loop counts pops per lane and rebuilds the quadruple of a lane that runs dry.
-    bool lean = ((count + 31) >> 5) <= 4;
+    // (a lane can contribute at most n elements to the n extremes: with n <= 4 the pops stay inside its quadruple by construction)
+    bool lean = ((count + 31) >> 5) <= 4 || n <= 4;
     if (!lean) {
         const unsigned ta = __reduce_max_sync(kFull, a3), tb = __reduce_max_sync(kFull, b3);
         const int ca = (a0 > ta ? 1 : 0) + (a1 > ta ? 1 : 0) + (a2 > ta ? 1 : 0);
