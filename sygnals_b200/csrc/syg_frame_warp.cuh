@@ -119,8 +119,10 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
 
     // STAGE 0: the plan tables (window, twiddles, mel taps: ~38 KB for n_fft 2048 / 128 mels) live in shared memory behind the
     // warps' regions -- 116 table loads per lane and frame become LDS with no L1 tag traffic and no misses
-    constexpr bool TBL = (STAGE == 0);
-    unsigned char* const tb = smem_raw + (size_t)WT::kWarps * WF * sizeof(float);
+    // STAGE 4 keeps window / twiddles / (full-scale) split twiddles there too, behind the per-warp tile blocks: its L1 pipe is the
+    // busiest unit (95 %) and 40 of its 56 loads per lane and task were table reads through the L1 tag stage
+    constexpr bool TBL = (STAGE == 0 || STAGE == 4);
+    unsigned char* const tb = smem_raw + ((size_t)WT::kWarps * WF + (STAGE == 4 ? (size_t)WT::kWarps * WB4 : 0)) * sizeof(float);
     const float2* const t_win = TBL ? reinterpret_cast<const float2*>(tb) : reinterpret_cast<const float2*>(a.window);
     const float2* const t_tw = TBL ? reinterpret_cast<const float2*>(tb + WT::kWinB) : a.tw;
     const float2* const t_twsh = TBL ? reinterpret_cast<const float2*>(tb + WT::kWinB + WT::kTwB) : a.twsh;
@@ -135,8 +137,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         // (consecutive k) read consecutive words instead of stride-r ones
         for (int i = tid; i < M; i += NT) d_tw[i] = __ldg(a.tw + (i / E) * (i % E));
         float2* d_twsh = const_cast<float2*>(t_twsh);
-        for (int i = tid; i <= M / 2; i += NT) d_twsh[i] = __ldg(a.twsh + i);
-        if (a.mask & syg::FB_MFCC) {
+        for (int i = tid; i <= M / 2; i += NT) d_twsh[i] = __ldg((STAGE == 4 ? a.tws : a.twsh) + i);
+        if (STAGE == 0 && (a.mask & syg::FB_MFCC)) {
             int4* d_sl = const_cast<int4*>(t_slots);
             for (int i = tid; i < a.n_mels; i += NT) d_sl[i] = __ldg(a.mel_slots + i);
             float4* d_mw = const_cast<float4*>(t_melw);
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 const int k = j + kk;
                 if (i == E / 2 && j != 0) break;
                 if (STAGE == 4) {
-                    const float2 w = __ldg(&a.tws[k]);
+                    const float2 w = t_twsh[k];
                     float xkr, xki, xmr, xmi;
                     real_split(zk[i].x, zk[i].y, zm[i].x, zm[i].y, w.x, w.y, xkr, xki, xmr, xmi);
                     const int slot = (int)(task & (SUBS - 1)) * FW + f;

@@ -22,7 +22,8 @@ static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, 
         const int TT = WT::kWarps * WT::FW;
         smem += (size_t)TT * sizeof(long long) + (size_t)(WT::M + 1) * (TT + 1) * (wide ? 8 : 4);
     }
-    if (STAGE == 4) smem += (size_t)WT::kWarps * (16 + (((WT::M + 1) * 9 + 1) & ~1)) * sizeof(float);   // per warp: 8 offsets + tile [B][9]
+    if (STAGE == 4) smem += (size_t)WT::kWarps * (16 + (((WT::M + 1) * 9 + 1) & ~1)) * sizeof(float)   // per warp: 8 offsets + tile [B][9]
+                            + WT::kWinB + WT::kTwB + WT::kTwshB;                                           // window, twiddles, split twiddles
     if (blocks_per_sm[wide] == 0 || smem > smem_seen[wide]) {
         smem_seen[wide] = smem;
         LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + (STAGE == 3 && !wide ? (WT::M + 1) * (WT::kWarps * WT::FW + 1) * 4 : 0)));
@@ -52,7 +53,10 @@ static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count,
         case 5: return frame_warp_t<FftTile<5, 8>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
         case 6: return frame_warp_t<FftTile<6, 8>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
         case 7: return frame_warp_t<FftTile<7, 16>, EXTRA, NT3, MINB3, STAGE>(a, sm_count, st, err);
-        case 8: return frame_warp_t<FftTile<8, 16>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
+        case 8:
+            // warp-private tiles + tables: 16 warps need 226 KB, which fits one 512-thread CTA per SM but not two 256-thread ones
+            if constexpr (STAGE == 4) return frame_warp_t<FftTile<8, 16>, EXTRA, 512, 1, STAGE>(a, sm_count, st, err);
+            else return frame_warp_t<FftTile<8, 16>, EXTRA, NT, MINB, STAGE>(a, sm_count, st, err);
         case 9:
             if constexpr (STAGE == 4) break;                          // warp-private tiles exist for M <= 256 only
             else return frame_warp_t<FftTile<9, 32>, EXTRA, NT3, MINB3, STAGE>(a, sm_count, st, err);
