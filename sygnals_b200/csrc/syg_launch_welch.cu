@@ -26,12 +26,11 @@ static int welch_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::
     return 0;
 }
 
-template <class TL>
+template <class TL, int NT = 256, int MINB = 2, bool TBLW = false>
 static int welch_warp_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err) {
-    constexpr int NT = 256;
-    using WW = sygdev::WelchWarpTile<TL, NT>;
+    using WW = sygdev::WelchWarpTile<TL, NT, TBLW>;
     static int blocks_per_sm = 0;
-    auto kfn = sygdev::welch_warp_kernel<TL, NT, 2>;
+    auto kfn = sygdev::welch_warp_kernel<TL, NT, MINB, TBLW>;
     if (blocks_per_sm == 0) {
         LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WW::bytes));
         int nb = 0;
@@ -58,7 +57,7 @@ int welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st, std:
             case 6: return welch_warp_t<FftTile<6, 8>>(a, sm_count, st, err);
             case 7: return welch_warp_t<FftTile<7, 16>>(a, sm_count, st, err);
             case 8: return welch_warp_t<FftTile<8, 16>>(a, sm_count, st, err);
-            case 9: return welch_warp_t<FftTile<9, 32>>(a, sm_count, st, err);
+            case 9: return welch_warp_t<FftTile<9, 32>, 512, 1, true>(a, sm_count, st, err);   // 16 warps + plan tables in one CTA (226 KB)
             case 10: return welch_warp_t<FftTile<10, 32>>(a, sm_count, st, err);
         }
     }

@@ -16,22 +16,26 @@
 
 namespace sygdev {
 
-template <class TL, int NT>
+// TBLW: window, twiddles and split twiddles live in shared memory behind the warps' regions (80 of the 111 loads per lane and
+// sub-segment are table reads; as LDS they skip the L1 tag stage).  Used where 16 warps + tables fit one CTA (M = 512: 226 KB, with
+// the accumulator pitch left unpadded).
+template <class TL, int NT, bool TBLW = false>
 struct WelchWarpTile {
     using WT = WarpTile<TL, NT>;
     static constexpr int FW = WT::FW, ZS = WT::ZS;
     // accumulator pitch: the FW lane groups of a warp add to their own accumulators in the same 32-bit shared-memory access, so the
     // groups (G = 32 / FW lanes each) must start G banks apart: pitch = G (mod 32), at least WarpTile::PS
-    static constexpr int PS = (FW == 1) ? WT::PS : ((WT::PS - WT::G + 31) / 32 * 32 + WT::G);
+    static constexpr int PS = (FW == 1 || TBLW) ? WT::PS : ((WT::PS - WT::G + 31) / 32 * 32 + WT::G);
     static constexpr int ZR = (2 * ZS + 3) / 4 * 4;                  // floats of one Z region
     static constexpr int warp_floats = FW * (ZR + PS);               // Z regions, then the accumulators
-    static constexpr size_t bytes = (size_t)WT::kWarps * warp_floats * sizeof(float);
+    static constexpr size_t table_bytes = TBLW ? (size_t)(2 * WT::M * 4 + WT::M * 8 + (WT::M / 2 + 1) * 8) : 0;
+    static constexpr size_t bytes = (size_t)WT::kWarps * warp_floats * sizeof(float) + table_bytes;
 };
 
-template <class TL, int NT, int MINB>
+template <class TL, int NT, int MINB, bool TBLW = false>
 __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchArgs a) {
     using WT = WarpTile<TL, NT>;
-    using WW = WelchWarpTile<TL, NT>;
+    using WW = WelchWarpTile<TL, NT, TBLW>;
     constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, PS = WW::PS, LE = WT::LOG2E;
     constexpr int Q = E / R2;
     constexpr int B = M + 1;
@@ -43,7 +47,18 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
     float2* const zs = reinterpret_cast<float2*>(wbase + f * WW::ZR);
     float* const accw = wbase + FW * WW::ZR;                          // [FW][PS], ppad layout
     float* const acc = accw + f * PS;
-    const float2* const w2 = reinterpret_cast<const float2*>(a.window);
+    float2* const tbw = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem_raw) + WT::kWarps * WW::warp_floats);   // [M] window, [M] tw, [M/2+1] tws
+    const float2* const w2 = TBLW ? tbw : reinterpret_cast<const float2*>(a.window);
+    const float2* const t_tw = TBLW ? tbw + M : a.tw;
+    const float2* const t_tws = TBLW ? tbw + 2 * M : a.tws;
+    if (TBLW) {
+        for (int i = tid; i < M; i += NT) {
+            tbw[i] = __ldg(reinterpret_cast<const float2*>(a.window) + i);
+            tbw[M + i] = __ldg(a.tw + i);
+        }
+        for (int i = tid; i <= M / 2; i += NT) tbw[2 * M + i] = __ldg(a.tws + i);
+        __syncthreads();
+    }
     const bool full = (a.nperseg == 2 * M);
     const float inv_n = 1.0f / (float)a.nperseg;
 
@@ -112,7 +127,7 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
             }
             SYG_UNROLL
             for (int r = 0; r < E; ++r) {
-                const float2 w = __ldg(w2 + j + r * G);               // zero beyond nperseg: padding samples vanish
+                const float2 w = TBLW ? w2[j + r * G] : __ldg(w2 + j + r * G);   // zero beyond nperseg: padding samples vanish
                 z[r] = make_float2((z[r].x - mean) * w.x, (z[r].y - mean) * w.y);
             }
             // ---------------- FFT (as in frame_warp_kernel) ----------------
@@ -133,7 +148,7 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                 const int k = b & (E - 1);
                 SYG_UNROLL
                 for (int r = 1; r < R2; ++r) {
-                    const float2 w = __ldg(&a.tw[r * k]);
+                    const float2 w = TBLW ? t_tw[r * k] : __ldg(&t_tw[r * k]);
                     cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
                 }
                 dft_dif_p<R2, 1>(z + q * R2);
@@ -161,7 +176,7 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                     const bool blk = ((M - kk) & (E - 1)) == 0;
                     float2 zm = blk ? zm1[c1] : zm0[c1];
                     if (i == 0 && j == 0) zm = zk;
-                    const float2 w = __ldg(&a.tws[k]);
+                    const float2 w = TBLW ? t_tws[k] : __ldg(&t_tws[k]);
                     float xkr, xki, xmr, xmi;
                     real_split(zk.x, zk.y, zm.x, zm.y, w.x, w.y, xkr, xki, xmr, xmi);
                     if (valid) {
