@@ -6,7 +6,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "sygnals_b200", "csrc")
-OUT = os.path.join(HERE, "libsygb200_emu.so")
+# SYG_EMU_ASAN=1: AddressSanitizer build (run the emu tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so) and
+# ASAN_OPTIONS=detect_leaks=0) -- the memory-safety check for the kernels' global / shared indexing on this GPU pool, where
+# compute-sanitizer is closed.
+ASAN = os.environ.get("SYG_EMU_ASAN", "") == "1"
+OUT = os.path.join(HERE, "libsygb200_emu_asan.so" if ASAN else "libsygb200_emu.so")
 
 
 def build_emu(force: bool = False) -> str:
@@ -15,13 +19,14 @@ def build_emu(force: bool = False) -> str:
     if not force and os.path.exists(OUT) and all(os.path.getmtime(p) <= os.path.getmtime(OUT) for p in deps):
         return OUT
     from concurrent.futures import ThreadPoolExecutor
-    objdir = os.path.join(ROOT, "build", "emu_obj")
+    objdir = os.path.join(ROOT, "build", "emu_obj_asan" if ASAN else "emu_obj")
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-O1"] if ASAN else []
     os.makedirs(objdir, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")] + [os.path.join(HERE, "syg_emu.cpp")]
 
     def cc(src):
         obj = os.path.join(objdir, os.path.basename(src).rsplit(".", 1)[0] + ".o")
-        cmd = ["g++", "-O2", "-std=c++17", "-DSYG_EMU", "-fPIC", "-pthread", "-I", HERE, "-I", CSRC, "-Wno-unused-value",
+        cmd = ["g++", "-O2", "-std=c++17", "-DSYG_EMU", "-fPIC", "-pthread", "-I", HERE, "-I", CSRC, "-Wno-unused-value"] + san + [
                "-c", "-o", obj, "-x", "c++", src]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -30,7 +35,7 @@ def build_emu(force: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
         objs = list(ex.map(cc, srcs))
-    r = subprocess.run(["g++", "-shared", "-pthread", "-o", OUT + ".tmp"] + objs, capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + ["-o", OUT + ".tmp"] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ (emulator link) failed:\n" + r.stdout + r.stderr[-6000:])
     os.replace(OUT + ".tmp", OUT)
