@@ -361,7 +361,8 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
                                   (double)p->contrast_quantile, b, err))
             return fail(SYG_E_BADARG, "%s", err.c_str());
         a.nb = b.nb;
-        for (int i = 0; i < b.nb; ++i) { a.band_lo[i] = b.lo[i]; a.band_cnt[i] = b.cnt[i]; a.band_n[i] = b.nq[i]; }
+        // the kernels rely on 1 <= band_n <= band_cnt for non-empty bands (sortedr[:idx] with idx > rows takes every row)
+        for (int i = 0; i < b.nb; ++i) { a.band_lo[i] = b.lo[i]; a.band_cnt[i] = b.cnt[i]; a.band_n[i] = std::max(1, std::min(b.nq[i], std::max(b.cnt[i], 1))); }
         pl.fin.nb = b.nb;
         ws += (size_t)T * 2 * b.nb * sizeof(float);
     }

@@ -544,14 +544,14 @@ SYG_DEVICE SYG_INLINE Sel4 track4(const float* __restrict__ q, int mine, int cou
 
 // rebuild a lane's descending quadruple from its elements below `last` (keys = bits ^ flip) plus the copies of `last`
 // it has not popped yet; popped = number of elements this lane has popped so far (they are its `popped` largest keys)
-SYG_DEVICE SYG_INLINE uint4 refill4(const float* __restrict__ q, int mine, unsigned flip, unsigned last, int popped) {
+SYG_DEVICE SYG_INLINE uint4 refill4(const float* __restrict__ q, int mine, unsigned flip, unsigned last, int popped, unsigned tag) {
     unsigned n0 = 0u, n1 = 0u, n2 = 0u, n3 = 0u;
     int ge = 0;
 #ifndef SYG_EMU
 #pragma unroll 1
 #endif
     for (int i = 0; i < mine; ++i) {
-        const unsigned x = __float_as_uint(q[36 * i]) ^ flip;
+        const unsigned x = ((__float_as_uint(q[36 * i]) ^ flip) & ~31u) | tag;
         ge += (x >= last) ? 1 : 0;
         ins4_desc(n0, n1, n2, n3, (x < last) ? x : 0u);
     }
@@ -602,14 +602,16 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
     } else {
         t = track4(q, mine, count);
     }
-    // both directions as "largest key first": top keys = bits, bottom keys = ~bits (0 = nothing)
-    unsigned a0 = t.a0, a1 = t.a1, a2 = t.a2, a3 = t.a3;
-    unsigned b0 = ~t.b0, b1 = ~t.b1, b2 = ~t.b2, b3 = ~t.b3;
+    // both directions as "largest key first": top keys = bits, bottom keys = ~bits (0 = nothing).  The low 5 bits of every key
+    // are replaced by the lane number: keys of different lanes never tie, so one REDUX names the single lane that pops and the
+    // pop needs no ballot / lowest-lane election (17 -> 8 instructions per popped element and direction).  The price is a
+    // selection and a value that are exact only down to 2^-18 relative (|X|^2; 2^-19 on the magnitude = 1.7e-5 dB, the parity
+    // bar is 1e-3 dB and the FP32 spectrum itself carries ~1e-6).
+    const unsigned tag = (unsigned)lane;
+    unsigned a0 = (t.a0 & ~31u) | tag, a1 = (t.a1 & ~31u) | tag, a2 = (t.a2 & ~31u) | tag, a3 = (t.a3 & ~31u) | tag;
+    unsigned b0 = (~t.b0 & ~31u) | tag, b1 = (~t.b1 & ~31u) | tag, b2 = (~t.b2 & ~31u) | tag, b3 = (~t.b3 & ~31u) | tag;
     int ra = n, rb = n;                                         // elements still to pop (warp uniform)
     float sa = 0.0f, sb = 0.0f;
-    // One REDUX per step picks the warp-wide extreme among the lanes' heads; every lane holding that value pops it (ties
-    // pop together and are counted by value, so silent frames finish in one step).  Pops are selects, not branches.
-    //
     // Untracked elements are <= their lane's 4th key <= T = max over lanes of the 4th keys, so the tracked keys above T
     // are exactly the largest elements of the band.  If there are at least n of them (the common case), the n pops never
     // leave the tracked quadruples and the lean loop needs no bookkeeping; otherwise (strongly clustered spectra) the
@@ -624,24 +626,21 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
         lean = (int)(cc & 0xffffu) >= n && (int)(cc >> 16) >= n;
     }
     if (lean) {
-        // one element per step and direction (the lowest lane holding the extreme pops), both directions in one
-        // straight-line body: two independent REDUX chains for the scheduler to interleave
-        const unsigned lt = (1u << lane) - 1u;
-        // (bulk rounds -- pop every head above the warp maximum of the second keys at once, ~7 per round -- were measured:
-        // two more REDUX per round cost more than the saved rounds, +1.3 % kernel time.  Rejected.)
+        // one element per step and direction, both directions in one straight-line body: two independent REDUX chains for the
+        // scheduler to interleave.  Pops are selects, not branches.
+        // (bulk rounds -- pop every head above the warp maximum of the second keys at once, ~7 per round -- were measured in
+        // round 1: two more REDUX per round cost more than the saved rounds, +1.3 % kernel time.  Rejected.)
 #ifndef SYG_EMU
 #pragma unroll 1
 #endif
         for (int it = 0; it < n; ++it) {
             const unsigned ga = __reduce_max_sync(kFull, a0);
             const unsigned gb = __reduce_max_sync(kFull, b0);
-            const bool ea = (a0 == ga), eb = (b0 == gb);
-            const unsigned ma = __ballot_sync(kFull, ea), mb = __ballot_sync(kFull, eb);
-            const bool oa = ea && (ma & lt) == 0u, ob = eb && (mb & lt) == 0u;
+            const bool oa = (a0 == ga), ob = (b0 == gb);
             sa += sqrt_approx(__uint_as_float(ga));
             sb += sqrt_approx(__uint_as_float(~gb));
-            a0 = oa ? a1 : a0; a1 = oa ? a2 : a1; a2 = oa ? a3 : a2; a3 = oa ? 0u : a3;
-            b0 = ob ? b1 : b0; b1 = ob ? b2 : b1; b2 = ob ? b3 : b2; b3 = ob ? 0u : b3;
+            a0 = oa ? a1 : a0; a1 = oa ? a2 : a1; a2 = oa ? a3 : a2; a3 = oa ? tag : a3;
+            b0 = ob ? b1 : b0; b1 = ob ? b2 : b1; b2 = ob ? b3 : b2; b3 = ob ? tag : b3;
         }
     } else {
         int ha = min(mine, 4), hb = ha;                         // tracked keys left
@@ -661,7 +660,7 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
                 ha -= own ? 1 : 0;
                 if (__any_sync(kFull, ha == 0 && pa < mine) && ra > 0) {
                     if (ha == 0 && pa < mine) {
-                        const uint4 v = refill4(q, mine, 0u, g, pa);
+                        const uint4 v = refill4(q, mine, 0u, g, pa, tag);
                         a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w;
                         ha = min(mine - pa, 4);
                     }
@@ -678,7 +677,7 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
                 hb -= own ? 1 : 0;
                 if (__any_sync(kFull, hb == 0 && pb < mine) && rb > 0) {
                     if (hb == 0 && pb < mine) {
-                        const uint4 v = refill4(q, mine, 0xffffffffu, g, pb);
+                        const uint4 v = refill4(q, mine, 0xffffffffu, g, pb, tag);
                         b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
                         hb = min(mine - pb, 4);
                     }

@@ -617,12 +617,15 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 const float* pp = pww + ff * RSS;
                 float pmx = 0.0f, vmx = 0.0f;
                 float mine_pv = 0.0f;                                   // lane bd keeps band bd's peak, lane nb + bd its valley
+                const int lane_v = lane - a.nb;
                 for (int bd = 0; bd < a.nb; ++bd) {
-                    float peak, valley;
-                    band_peak_valley_any(pp, a.band_lo[bd], a.band_cnt[bd], a.band_n[bd], peak, valley);
-                    mine_pv = (lane == bd) ? peak : ((lane == a.nb + bd) ? valley : mine_pv);
-                    pmx = fmaxf(pmx, peak);                             // fmaxf drops the NaN of an empty band
-                    vmx = fmaxf(vmx, valley);
+                    const int cnt = a.band_cnt[bd];                     // 1 <= band_n <= band_cnt is guaranteed by the plan (syg_api.cu)
+                    float2 pv = make_float2(__uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u));   // empty band: mean of nothing -> NaN (numpy)
+                    if (cnt > 0) pv = band_peak_valley_stream(pp, a.band_lo[bd], cnt, a.band_n[bd]);
+                    mine_pv = (lane == bd) ? pv.x : mine_pv;
+                    mine_pv = (lane_v == bd) ? pv.y : mine_pv;
+                    pmx = fmaxf(pmx, pv.x);                             // fmaxf drops the NaN of an empty band
+                    vmx = fmaxf(vmx, pv.y);
                 }
                 if (lane < 2 * a.nb) a.cws[gff * (2 * a.nb) + lane] = mine_pv;   // one coalesced store per frame (nb <= kMaxBands = 12)
                 const long long uff = __shfl_sync(kFull, u, ff * G);    // unit of frame ff (all lanes take part)
