@@ -44,6 +44,20 @@ int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(e_));                                                   \
     } while (0)
 
+// every entry point runs on its context's device and gives the caller's current device back on return
+struct DeviceGuard {
+    int prev = -1, dev;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int d) : dev(d) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+#define ENTER_DEVICE(ctx)                                                                                          \
+    DeviceGuard dg_((ctx)->device);                                                                                \
+    if (dg_.err != cudaSuccess) return fail(SYG_E_CUDA, "cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(dg_.err))
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -76,6 +90,7 @@ struct syg_ctx {
     std::map<std::string, void*> tables;
     std::map<std::string, std::vector<int>> host_ints;
     DevBuf ws;                      // workspace of the device-pointer entry points
+    cudaEvent_t ws_done = nullptr;  // recorded after the last kernel that uses `ws`: the next call (any stream) waits on it
     Lane lanes[2];
     // optional per-kernel timing (syg_ctx_profile_*): event pairs around every launch, summed on read
     bool prof_on = false;
@@ -109,10 +124,14 @@ template <class T>
 int upload_table(syg_ctx* ctx, const std::string& key, const std::vector<T>& host, const T** out) {
     auto it = ctx->tables.find(key);
     if (it != ctx->tables.end()) { *out = reinterpret_cast<const T*>(it->second); return SYG_OK; }
+    if (host.empty()) return fail(SYG_E_CUDA, "plan table %s was not built (internal error)", key.c_str());
     void* d = nullptr;
-    size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
-    CK(cudaMalloc(&d, bytes));
-    if (!host.empty()) CK(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d, host.size() * sizeof(T)));
+    // Pageable-memory cudaMemcpy may return before the DMA has landed and is ordered only against the legacy default stream; the
+    // kernels run on the caller's (possibly non-blocking) stream, so wait here: tables are built once per plan.
+    cudaError_t e = cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+    if (e != cudaSuccess) { cudaFree(d); return fail(SYG_E_CUDA, "plan table upload (%s): %s", key.c_str(), cudaGetErrorString(e)); }
     ctx->tables[key] = d;
     *out = reinterpret_cast<const T*>(d);
     return SYG_OK;
@@ -131,12 +150,14 @@ int get_fft_tables(syg_ctx* ctx, int n_fft, const float2** tw, const float2** tw
     const int M = n_fft / 2;
     std::string k1 = keyf("tw:%d", n_fft), k2 = keyf("tws:%d", n_fft);
     std::vector<float2> a, b;
-    if (!ctx->tables.count(k1)) {
+    if (!ctx->tables.count(k1)) {                                   // each table under its own key: a failed upload of one cannot poison the other
         a.resize(M);
         for (int k = 0; k < M; ++k) {
             const double ang = -2.0 * sygplan::kPi * (double)k / (double)M;
             a[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
         }
+    }
+    if (!ctx->tables.count(k2)) {
         b.resize(M / 2 + 1);
         for (int k = 0; k <= M / 2; ++k) {
             const double ang = -2.0 * sygplan::kPi * (double)k / (double)n_fft;
@@ -656,7 +677,8 @@ int syg_ctx_create(int device, syg_ctx** out) {
         return fail(SYG_E_CUDA, "no CUDA device available (%s); sygb200 has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     if (device < 0 || device >= n) return fail(SYG_E_BADARG, "device %d out of range (0..%d)", device, n - 1);
-    CK(cudaSetDevice(device));
+    DeviceGuard dg_(device);
+    if (dg_.err != cudaSuccess) return fail(SYG_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(dg_.err));
     syg_ctx* c = new syg_ctx();
     c->device = device;
     e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -667,10 +689,11 @@ int syg_ctx_create(int device, syg_ctx** out) {
 
 void syg_ctx_destroy(syg_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dg_(ctx->device);
     cudaDeviceSynchronize();
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     ctx->ws.release();
+    if (ctx->ws_done) cudaEventDestroy(ctx->ws_done);
     for (auto& l : ctx->lanes) {
         l.in.release(); l.in16.release(); l.out0.release(); l.out1.release(); l.starts.release(); l.valid.release(); l.ws.release();
         if (l.stream) cudaStreamDestroy(l.stream);
@@ -698,7 +721,7 @@ int syg_ctx_profile_enable(syg_ctx* ctx, int on) {
 int syg_ctx_profile_read(syg_ctx* ctx, double* ms, int64_t* launches, int reset) {
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     for (auto& pp : ctx->prof_pairs) {
         float t = 0.0f;
         CK(cudaEventSynchronize(pp.b));
@@ -756,7 +779,7 @@ int syg_features_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, c
     int rc = check_units(units);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     FeaturePlan pl;
     if ((rc = build_feature_plan(ctx, units, p, pl))) return rc;
     if (units->n_units == 0 || pl.T <= 0 || pl.n_rows == 0) return SYG_OK;
@@ -765,7 +788,13 @@ int syg_features_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, c
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     long long chunk = std::max<long long>(1, (long long)(ctx->ws_limit / std::max<size_t>(pl.ws_per_unit, 1)));
     chunk = std::min<long long>(chunk, units->n_units);
+    // the workspace is shared by every call on this context: order this call's kernels behind the previous user's, whatever
+    // stream that was (calls on ONE stream are ordered anyway; two streams would otherwise overwrite each other's mel energies)
+    if (ctx->ws_done) CK(cudaStreamWaitEvent(st, ctx->ws_done, 0));
+    else CK(cudaEventCreateWithFlags(&ctx->ws_done, cudaEventDisableTiming));
+    if (features_ws_bytes(pl, chunk) > ctx->ws.cap) CK(cudaStreamSynchronize(st));   // growing frees the old block: nothing may still use it
     if ((rc = ctx->ws.ensure(features_ws_bytes(pl, chunk)))) return rc;
+    struct Done { syg_ctx* c; cudaStream_t s; ~Done() { cudaEventRecord(c->ws_done, s); } } done_{ctx, st};
     for (long long u0 = 0; u0 < units->n_units; u0 += chunk) {
         const long long n = std::min(chunk, units->n_units - u0);
         syg::UnitGeom g = geom_of(units, u0, n);
@@ -781,7 +810,7 @@ static int features_host_impl(syg_ctx* ctx, const void* y_host, bool pcm16, cons
     int rc = check_host_units(units);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     FeaturePlan pl;
     if ((rc = build_feature_plan(ctx, units, p, pl))) return rc;
     if (units->n_units == 0 || pl.T <= 0 || pl.n_rows == 0) return SYG_OK;
@@ -812,7 +841,7 @@ int syg_features_host_pcm16(syg_ctx* ctx, const int16_t* y_host, const syg_units
 int syg_pcm16_to_f32(syg_ctx* ctx, const int16_t* in_dev, float* out_dev, int64_t n, void* stream) {
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     if (n < 0 || (n > 0 && (!in_dev || !out_dev))) return fail(SYG_E_BADARG, "bad pcm16 buffer");
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     std::string err;
     const int rc = syglaunch::pcm16_to_f32(reinterpret_cast<const short*>(in_dev), out_dev, n, ctx->sm_count,
                                            reinterpret_cast<cudaStream_t>(stream), err);
@@ -828,7 +857,7 @@ int syg_stft_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, int32
     int rc = check_units(units);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     syg::FrameArgs a;
     if ((rc = stft_setup(ctx, units, n_fft, hop_length, win_length, window, center, pad_mode, out_kind, a))) return rc;
     if (units->n_units == 0 || a.T <= 0) return SYG_OK;
@@ -849,7 +878,7 @@ int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units,
     int rc = check_host_units(units);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     syg::FrameArgs a;
     if ((rc = stft_setup(ctx, units, n_fft, hop_length, win_length, window, center, pad_mode, out_kind, a))) return rc;
     if (units->n_units == 0 || a.T <= 0) return SYG_OK;
@@ -875,7 +904,7 @@ int syg_psd_welch_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, 
     int rc = check_units(units);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     WelchPlan pl;
     if ((rc = welch_setup(ctx, units, fs, window, nperseg, noverlap, nfft, detrend_constant, scaling, pl))) return rc;
     if (units->n_units == 0) return SYG_OK;
@@ -895,7 +924,7 @@ int syg_psd_welch_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* u
     int rc = check_host_units(units);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     WelchPlan pl;
     if ((rc = welch_setup(ctx, units, fs, window, nperseg, noverlap, nfft, detrend_constant, scaling, pl))) return rc;
     if (units->n_units == 0) return SYG_OK;
@@ -923,7 +952,7 @@ int syg_aggregate_f32(syg_ctx* ctx, const float* feats_dev, int64_t n_seg, int32
     if (!feats_dev || !out_dev || !agg) return fail(SYG_E_BADARG, "NULL pointer");
     for (int i = 0; i < n_rows && i < 64; ++i)
         if (agg[i] < SYG_AGG_MEAN || agg[i] > SYG_AGG_MAX) return fail(SYG_E_BADARG, "unknown aggregation id %d", agg[i]);
-    CK(cudaSetDevice(ctx->device));
+    ENTER_DEVICE(ctx);
     std::string err;
     const int rc = syglaunch::aggregate(feats_dev, n_seg, n_rows, row_stride, reinterpret_cast<const long long*>(seg_off_dev), seg_len_dev,
                                         fixed_len, agg, out_dev, ctx->sm_count, reinterpret_cast<cudaStream_t>(stream), err);

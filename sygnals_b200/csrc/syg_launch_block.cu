@@ -10,15 +10,10 @@ namespace syglaunch {
 template <class TL, int MODE>
 static int frame_block_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using SM = sygdev::FrameSmem<TL>;
-    static int blocks_per_sm = 0;
+    static KernelCache kc;
     auto kfn = sygdev::frame_kernel<TL, MODE>;
-    if (blocks_per_sm == 0) {
-        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
-        int nb = 0;
-        LCK(SYG_OCCUPANCY(nb, kfn, sygdev::kThreads, SM::bytes));
-        if (nb < 1) { err = "frame kernel does not fit on an SM"; return -3; }
-        blocks_per_sm = nb;
-    }
+    int blocks_per_sm = 0;
+    if (int rc = prepare_kernel(kfn, sygdev::kThreads, SM::bytes, 0, kc, &blocks_per_sm, err)) return rc;
     const long long n_rounds = (a.n_frames + TL::F - 1) / TL::F;
     if (n_rounds <= 0) return 0;
     const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm);
@@ -32,16 +27,9 @@ static int stft_tile_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, s
     using SM = sygdev::StftTileSmem<TL, TT>;
     auto kfn = sygdev::stft_tile_kernel<TL, TT>;
     const size_t smem = SM::bytes(a.out_kind == 0);
-    static size_t opted = 0;
-    static int blocks_per_sm = 1;
-    if (smem > opted) {
-        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        opted = smem;
-        int nb = 0;
-        LCK(SYG_OCCUPANCY(nb, kfn, sygdev::kThreads, smem));
-        if (nb < 1) { err = "stft tile kernel does not fit on an SM"; return -3; }
-        blocks_per_sm = nb;
-    }
+    static KernelCache kc[2];                                       // occupancy differs between the float and the complex tile
+    int blocks_per_sm = 0;
+    if (int rc = prepare_kernel(kfn, sygdev::kThreads, smem, SM::bytes(true), kc[a.out_kind == 0], &blocks_per_sm, err)) return rc;
     const long long n_tiles = (a.n_frames + TT - 1) / TT;
     if (n_tiles <= 0) return 0;
     const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * blocks_per_sm);
@@ -81,13 +69,11 @@ int frame_block(int n_fft, int mode, const syg::FrameArgs& a, int sm_count, cuda
 }
 
 int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err) {
-#ifndef SYG_EMU
-    static size_t opted = 48 * 1024;                // float64 S_db tile: 32 x (n_mels + 1) x 8 B exceeds 48 KB for n_mels > 191
-    if (smem > opted) {
-        LCK(cudaFuncSetAttribute(sygdev::finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        opted = smem;
+    if (smem > 48 * 1024) {                         // the S_db tile exceeds the default 48 KB for wide mel banks
+        static KernelCache kc;
+        int nb = 0;
+        if (int rc = prepare_kernel(sygdev::finalize_kernel, sygdev::kThreads, smem, 0, kc, &nb, err)) return rc;
     }
-#endif
     SYG_LAUNCH(sygdev::finalize_kernel, dim3(grid_x, grid_y), dim3(sygdev::kThreads), smem, st, a);
     LCK(cudaGetLastError());
     return 0;

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 
 #include "syg_launch.h"
@@ -20,4 +21,36 @@
 
 namespace syglaunch {
 inline int ilog2i(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the occupancy result are PER DEVICE: one process may drive several GPUs
+// (one syg_ctx each, possibly from several threads), so every kernel instantiation keeps one slot per device behind a mutex.
+constexpr int kMaxDevices = 64;
+struct KernelCache {
+    std::mutex mu;
+    size_t opted[kMaxDevices] = {};
+    int blocks[kMaxDevices] = {};
+};
+
+// Makes `kfn` launchable with `smem` bytes of dynamic shared memory on the CURRENT device and returns the resident CTAs per SM
+// for (threads, smem) in *blocks.  attr_smem >= smem: opt in for more than this launch needs (variants that share a kernel).
+template <class K>
+inline int prepare_kernel(K kfn, int threads, size_t smem, size_t attr_smem, KernelCache& kc, int* blocks, std::string& err) {
+    int dev = 0;
+    LCK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) { err = "device index out of range"; return -3; }
+    std::lock_guard<std::mutex> lk(kc.mu);
+    if (attr_smem < smem) attr_smem = smem;
+    if (kc.blocks[dev] == 0 || attr_smem > kc.opted[dev]) {
+        if (attr_smem > kc.opted[dev]) {
+            LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_smem));
+            kc.opted[dev] = attr_smem;
+        }
+        int nb = 0;
+        LCK(SYG_OCCUPANCY(nb, kfn, threads, smem));
+        if (nb < 1) { err = "kernel does not fit on an SM"; return -3; }
+        kc.blocks[dev] = nb;
+    }
+    *blocks = kc.blocks[dev];
+    return 0;
+}
 }

@@ -12,30 +12,37 @@ namespace syglaunch {
 template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
 static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using WT = sygdev::WarpTile<TL, NT>;
-    static int blocks_per_sm[2] = {0, 0};
-    static size_t smem_seen[2] = {0, 0};
     auto kfn = sygdev::frame_warp_kernel<TL, EXTRA, NT, MINB, STAGE>;
     size_t smem = (size_t)WT::kWarps * WT::FW * WT::RS * sizeof(float);
     const int wide = (STAGE == 3 && a.out_kind == 0) ? 1 : 0;        // complex64 tile
+    size_t attr = 0;
     if (STAGE == 0) smem += WT::table_bytes(a.n_mels, (a.mask & syg::FB_MFCC) ? a.mel_pw_f4 : 0);
     if (STAGE == 3) {
         const int TT = WT::kWarps * WT::FW;
         smem += (size_t)TT * sizeof(long long) + (size_t)(WT::M + 1) * (TT + 1) * (wide ? 8 : 4);
+        attr = smem + (wide ? 0 : (size_t)(WT::M + 1) * (TT + 1) * 4);   // opt in once for the complex tile too
     }
     if (STAGE == 4) smem += (size_t)WT::kWarps * (16 + (((WT::M + 1) * 9 + 1) & ~1)) * sizeof(float)   // per warp: 8 offsets + tile [B][9]
                             + WT::kWinB + WT::kTwB + WT::kTwshB;                                           // window, twiddles, split twiddles
-    if (blocks_per_sm[wide] == 0 || smem > smem_seen[wide]) {
-        smem_seen[wide] = smem;
-        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + (STAGE == 3 && !wide ? (WT::M + 1) * (WT::kWarps * WT::FW + 1) * 4 : 0)));
-        int nb = 0;
-        LCK(SYG_OCCUPANCY(nb, kfn, NT, smem));
-        if (nb < 1) { err = "frame_warp kernel does not fit on an SM"; return -3; }
-        blocks_per_sm[wide] = nb;
+    // the dynamic size depends on the plan (n_mels, tap count): one cache slot per device and per (wide) variant; a larger request
+    // re-opts and re-measures occupancy (prepare_kernel)
+    static KernelCache kc[2];
+    static size_t smem_seen[2][kMaxDevices] = {};
+    int bps = 0;
+    {
+        int dev = 0;
+        LCK(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < kMaxDevices) {
+            std::lock_guard<std::mutex> lk(kc[wide].mu);
+            if (smem != smem_seen[wide][dev]) { kc[wide].blocks[dev] = 0; smem_seen[wide][dev] = smem; }   // occupancy is a function of smem
+        }
     }
+    if (int rc = prepare_kernel(kfn, NT, smem, attr, kc[wide], &bps, err)) return rc;
+    const int blocks_per_sm_w = bps;
     const long long per_cta = (long long)((STAGE == 4) ? 8 : WT::FW) * WT::kWarps;
     const long long n_rounds = (a.n_frames + per_cta - 1) / per_cta;
     if (n_rounds <= 0) return 0;
-    const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm[wide]);
+    const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm_w);
     SYG_LAUNCH(kfn, grid, NT, smem, st, a);
     LCK(cudaGetLastError());
     return 0;

@@ -10,15 +10,10 @@ namespace syglaunch {
 template <class TL>
 static int welch_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using SM = sygdev::WelchSmem<TL>;
-    static int blocks_per_sm = 0;
+    static KernelCache kc;
     auto kfn = sygdev::welch_kernel<TL>;
-    if (blocks_per_sm == 0) {
-        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
-        int nb = 0;
-        LCK(SYG_OCCUPANCY(nb, kfn, sygdev::kThreads, SM::bytes));
-        if (nb < 1) { err = "welch kernel does not fit on an SM"; return -3; }
-        blocks_per_sm = nb;
-    }
+    int blocks_per_sm = 0;
+    if (int rc = prepare_kernel(kfn, sygdev::kThreads, SM::bytes, 0, kc, &blocks_per_sm, err)) return rc;
     if (a.g.n_units <= 0) return 0;
     const int grid = (int)std::min<long long>(a.g.n_units, (long long)sm_count * blocks_per_sm);
     SYG_LAUNCH(kfn, grid, sygdev::kThreads, SM::bytes, st, a);
@@ -29,15 +24,10 @@ static int welch_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::
 template <class TL, int NT = 256, int MINB = 2, bool TBLW = false>
 static int welch_warp_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using WW = sygdev::WelchWarpTile<TL, NT, TBLW>;
-    static int blocks_per_sm = 0;
+    static KernelCache kc;
     auto kfn = sygdev::welch_warp_kernel<TL, NT, MINB, TBLW>;
-    if (blocks_per_sm == 0) {
-        LCK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WW::bytes));
-        int nb = 0;
-        LCK(SYG_OCCUPANCY(nb, kfn, NT, WW::bytes));
-        if (nb < 1) { err = "welch_warp kernel does not fit on an SM"; return -3; }
-        blocks_per_sm = nb;
-    }
+    int blocks_per_sm = 0;
+    if (int rc = prepare_kernel(kfn, NT, WW::bytes, 0, kc, &blocks_per_sm, err)) return rc;
     if (a.g.n_units <= 0) return 0;
     const long long want = (a.g.n_units + NT / 32 - 1) / (NT / 32);
     const int grid = (int)std::min<long long>(want, (long long)sm_count * blocks_per_sm);

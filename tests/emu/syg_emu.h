@@ -59,6 +59,7 @@ static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
+#define cudaStreamLegacy ((cudaStream_t)0x1)
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2,
                       cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
