@@ -355,9 +355,17 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         if ((rc = upload_table(ctx, key + ":ps", slots, &a.mel_slots))) return rc;
         if ((rc = upload_table(ctx, key + ":pw", ms.w, &a.mel_pw))) return rc;
         {
-            std::string kn = key + ":pwn";                       // float4 count of the tap table (host side cache)
-            if (!ctx->host_ints.count(kn)) ctx->host_ints[kn] = std::vector<int>{(int)(ms.w.size() / 4)};
-            a.mel_pw_f4 = ctx->host_ints[kn][0];
+            std::string kn = key + ":pwn";                       // host side cache: float4 count of the tap table, then the sweep lengths
+            if (!ctx->host_ints.count(kn)) {
+                const int gs = fl <= 2048 ? 32 / warp_fw(fl) : 32;
+                std::vector<int> hv{(int)(ms.w.size() / 4)};
+                for (int g0 = 0; g0 < p->n_mels; g0 += gs) hv.push_back(ms.desc[(size_t)g0 * 4 + 2]);
+                ctx->host_ints[kn] = hv;
+            }
+            const std::vector<int>& hv = ctx->host_ints[kn];
+            a.mel_pw_f4 = hv[0];
+            a.mel_nsweeps = (int)hv.size() - 1 <= 8 ? (int)hv.size() - 1 : 0;
+            for (int i = 0; i < a.mel_nsweeps; ++i) a.mel_steps[i] = hv[1 + i];
         }
         a.n_mels = p->n_mels;
         a.mel_power_is_2 = (p->power == 2.0);

@@ -18,6 +18,14 @@ namespace sygdev {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// loop unrolling by a compile-time factor (1 = keep the loop): the band-specialised kernels pass their trip counts as constants
+#ifdef SYG_EMU
+#define SYG_UNROLL_BY(n)
+#else
+#define SYG_PRAGMA_(x) _Pragma(#x)
+#define SYG_UNROLL_BY(n) SYG_PRAGMA_(unroll n)
+#endif
+
 // --------------------------------------------------------------------------------------------------------
 // shared-memory access wrappers (bank accounting in the emulator build; plain ld/st in the CUDA build)
 // --------------------------------------------------------------------------------------------------------
@@ -507,16 +515,16 @@ struct Sel4 {                        // one lane's view of a band: four largest 
 // stream this lane's `mine` elements (q[36 i]) once, keeping both sorted quadruples.  Elements are taken four at a time:
 // a 5-exchange sorting network orders the quad, two bitonic half-merges fold it into the lists (8.5 min/max per element
 // instead of 14 for element-wise insertion).
+template <bool ST>
 SYG_DEVICE SYG_INLINE Sel4 track4(const float* __restrict__ q, int mine, int count) {
+    constexpr int UQ = ST ? 8 : 1, US = ST ? 4 : 1;             // static band layout: trip counts are constants -> straight-line code
     Sel4 t;
     t.a0 = t.a1 = t.a2 = t.a3 = 0u;
     t.b0 = t.b1 = t.b2 = t.b3 = 0xffffffffu;
     // warp-uniform trip counts: every lane owns at least count/32 elements and at most one more
     const int nq = (count >> 5) >> 2;                           // full quads every lane has
     const int nmax = (count + 31) >> 5;
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
+    SYG_UNROLL_BY(UQ)
     for (int i = 0; i < nq; ++i) {
         const float* e = q + 144 * i;
         unsigned s0 = __float_as_uint(e[0]), s1 = __float_as_uint(e[36]), s2 = __float_as_uint(e[72]), s3 = __float_as_uint(e[108]);
@@ -530,9 +538,7 @@ SYG_DEVICE SYG_INLINE Sel4 track4(const float* __restrict__ q, int mine, int cou
         cex(m0, m2); cex(m1, m3); cex(m0, m1); cex(m2, m3);
         t.b0 = m0; t.b1 = m1; t.b2 = m2; t.b3 = m3;
     }
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
+    SYG_UNROLL_BY(US)
     for (int i = 4 * nq; i < nmax; ++i) {                        // <= 4 steps; the last one may be missing in some lanes
         const bool have = i < mine;
         const unsigned x = have ? __float_as_uint(q[36 * i]) : 0u;
@@ -559,8 +565,11 @@ SYG_DEVICE SYG_INLINE uint4 refill4(const float* __restrict__ q, int mine, unsig
     return make_uint4(n0, n1, n2, n3);
 }
 
-// returns {peak, valley}: mean of sqrt over the n largest / n smallest values of the band
+// returns {peak, valley}: mean of sqrt over the n largest / n smallest values of the band.  ST: (lo, count, n) are compile-time
+// constants at the call site (band-specialised kernel): every loop below unrolls completely.
+template <bool ST>
 SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p, int lo, int count, int n) {
+    constexpr int UP = ST ? 32 : 1;
     const int lane = threadIdx.x & 31;
     const float* q = p + ppad(lo + lane);
     const int mine = max((count - lane + 31) >> 5, 0);         // elements this lane owns
@@ -573,13 +582,13 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
             mx = max(x0, x1);
             mn = min(h0 ? x0 : 0xffffffffu, h1 ? x1 : 0xffffffffu);
         } else {
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
-            for (int i = 0; i < mine; ++i) {
-                const unsigned x = __float_as_uint(q[36 * i]);
+            const int nmax = (count + 31) >> 5;                 // warp-uniform trip count; the last element may be missing in some lanes
+            SYG_UNROLL_BY(UP)
+            for (int i = 0; i < nmax; ++i) {
+                const bool have = i < mine;
+                const unsigned x = have ? __float_as_uint(q[36 * i]) : 0u;
                 mx = max(mx, x);
-                mn = min(mn, x);
+                mn = min(mn, have ? x : 0xffffffffu);
             }
         }
         r.x = sqrt_approx(__uint_as_float(__reduce_max_sync(kFull, mx)));
@@ -600,7 +609,7 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
         cex(r0, r1); cex(r2, r3); cex(r0, r2); cex(r1, r3); cex(r1, r2);
         t.b0 = r0; t.b1 = r1; t.b2 = r2; t.b3 = r3;
     } else {
-        t = track4(q, mine, count);
+        t = track4<ST>(q, mine, count);
     }
     // both directions as "largest key first": top keys = bits, bottom keys = ~bits (0 = nothing).  The low 5 bits of every key
     // are replaced by the lane number: keys of different lanes never tie, so one REDUX names the single lane that pops and the
@@ -630,9 +639,7 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
         // scheduler to interleave.  Pops are selects, not branches.
         // (bulk rounds -- pop every head above the warp maximum of the second keys at once, ~7 per round -- were measured in
         // round 1: two more REDUX per round cost more than the saved rounds, +1.3 % kernel time.  Rejected.)
-#ifndef SYG_EMU
-#pragma unroll 1
-#endif
+        SYG_UNROLL_BY(UP)
         for (int it = 0; it < n; ++it) {
             const unsigned ga = __reduce_max_sync(kFull, a0);
             const unsigned gb = __reduce_max_sync(kFull, b0);
@@ -694,7 +701,7 @@ SYG_DEVICE SYG_INLINE void band_peak_valley_any(const float* __restrict__ p, int
     if (count <= 0) { peak = valley = __uint_as_float(0x7fc00000u); return; }     // mean of nothing -> NaN (numpy)
     if (n > count) n = count;
     if (n < 1) n = 1;
-    const float2 r = band_peak_valley_stream(p, lo, count, n);
+    const float2 r = band_peak_valley_stream<false>(p, lo, count, n);
     peak = r.x;
     valley = r.y;
 }

@@ -51,6 +51,40 @@ struct WarpTile {
 template <int LOG2E>
 SYG_DEVICE SYG_INLINE int zpad(int i) { return i + (i >> LOG2E); }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Plan specialisations of the feature kernel (n_fft 2048).  The spectral-contrast band layout and the mel sweep lengths are plan
+// constants; for the layouts below they are ALSO compile-time constants, so the band loop, the selection networks, the pop loops
+// and the mel sweeps unroll into straight-line code (no per-band loop overhead, no trip-count loads, no convergence checks in
+// front of the warp reductions).  The launcher (syg_launch_warp.h) compares the run-time plan with the spec and falls back to
+// SpecNone (the generic loops) on any difference.
+//   band(i, 0..2) = {first bin, bins, quantile count}  of sygplan::build_bands(sr, 2048, n_bands=6, fmin=200, quantile=0.02)
+//   steps(i)      = float4 steps of mel sweep i of sygplan::build_mel_slots (n_mels = 128, fmin 0, fmax sr/2, 32 filters per sweep)
+// ---------------------------------------------------------------------------------------------------------------------------
+struct SpecNone {
+    static constexpr bool kBands = false, kMel = false;
+    static constexpr int nb = 0, n_sweeps = 0;
+    SYG_HD static constexpr int band(int, int) { return 0; }
+    SYG_HD static constexpr int steps(int) { return 0; }
+};
+struct Spec44k {                                                       // sr 44100 (BASELINE cfg4)
+    static constexpr bool kBands = true, kMel = true;
+    static constexpr int nb = 7, n_sweeps = 4;
+    SYG_HD static constexpr int band(int i, int f) {
+        constexpr int t[7][3] = {{0, 9, 1}, {9, 9, 1}, {18, 19, 1}, {37, 37, 1}, {74, 74, 2}, {148, 149, 3}, {297, 728, 15}};
+        return t[i][f];
+    }
+    SYG_HD static constexpr int steps(int i) { constexpr int t[4] = {22, 8, 6, 6}; return t[i]; }
+};
+struct Spec22k {                                                       // sr 22050 (the reference's default sample rate; BASELINE cfg1)
+    static constexpr bool kBands = true, kMel = true;
+    static constexpr int nb = 7, n_sweeps = 4;
+    SYG_HD static constexpr int band(int i, int f) {
+        constexpr int t[7][3] = {{0, 18, 1}, {18, 19, 1}, {37, 37, 1}, {74, 74, 2}, {148, 149, 3}, {297, 297, 6}, {594, 431, 9}};
+        return t[i][f];
+    }
+    SYG_HD static constexpr int steps(int i) { constexpr int t[4] = {16, 8, 6, 4}; return t[i]; }
+};
+
 template <int G>
 SYG_DEVICE SYG_INLINE float lanes_sum(float v) {
     SYG_UNROLL
@@ -86,7 +120,7 @@ SYG_DEVICE SYG_INLINE double lanes_scan_incl(double v, int gl) {
 // (A two-launch variant -- FFT kernel + 64-register epilogue kernel with the spectra handed over through a workspace -- was
 // measured and removed: +4 % at best, see DESIGN.md 4.1 and profiles/r01_t_two_stage_ncu_summary.txt.  CTA barriers between
 // the phases of the fused kernel were measured too: +8 % time.)
-template <class TL, bool EXTRA, int NT, int MINB, int STAGE>
+template <class TL, bool EXTRA, int NT, int MINB, int STAGE, class SP = SpecNone>
 __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameArgs a) {
     using WT = WarpTile<TL, NT>;
     constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, ZS = WT::ZS, PS = WT::PS, LE = WT::LOG2E;
@@ -558,6 +592,30 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             const float* pfr = pww + mf * RSS;
             const float4* const mw4 = t_melw;
             float fmx = 0.0f;
+            if constexpr (SP::kMel && FW == 1) {
+                // plan-specialised sweeps: n_mels = 32 * n_sweeps, every trip count and tap offset is a constant
+                int goff = 0;
+                SYG_UNROLL
+                for (int sw = 0; sw < SP::n_sweeps; ++sw) {
+                    const int4 d = t_slots[sw * 32 + sl];                // {filter, first padded word, steps, tap offset}
+                    const float4* wv = mw4 + goff + sl;
+                    const float4* pp4 = reinterpret_cast<const float4*>(pfr + d.y);
+                    float2 m01 = make_float2(0.0f, 0.0f), m23 = m01;
+                    SYG_UNROLL
+                    for (int i = 0; i < SP::steps(sw); ++i) {
+                        const float4 w = wv[32 * i];
+                        const float4 q = pp4[i];
+                        m01 = __ffma2_rn(make_float2(w.x, w.y), make_float2(q.x, q.y), m01);
+                        m23 = __ffma2_rn(make_float2(w.z, w.w), make_float2(q.z, q.w), m23);
+                    }
+                    const float acc = (m01.x + m01.y) + (m23.x + m23.y);
+                    if (fvalid) {
+                        a.melws[gmf * a.n_mels + d.x] = acc;
+                        fmx = fmaxf(fmx, acc);
+                    }
+                    goff += 32 * SP::steps(sw);
+                }
+            } else
             for (int base = 0; base < a.n_mels; base += GS) {
                 const int slot = min(base + sl, a.n_mels - 1);
                 const int4 d = TBL ? t_slots[slot] : __ldg(&t_slots[slot]);   // {filter, first padded word, steps, tap offset}: steps/offset are warp uniform
@@ -618,10 +676,20 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 float pmx = 0.0f, vmx = 0.0f;
                 float mine_pv = 0.0f;                                   // lane bd keeps band bd's peak, lane nb + bd its valley
                 const int lane_v = lane - a.nb;
+                if constexpr (SP::kBands) {
+                    SYG_UNROLL
+                    for (int bd = 0; bd < SP::nb; ++bd) {               // compile-time band layout: (lo, count, n) fold into the code
+                        const float2 pv = band_peak_valley_stream<true>(pp, SP::band(bd, 0), SP::band(bd, 1), SP::band(bd, 2));
+                        mine_pv = (lane == bd) ? pv.x : mine_pv;
+                        mine_pv = (lane == SP::nb + bd) ? pv.y : mine_pv;
+                        pmx = fmaxf(pmx, pv.x);
+                        vmx = fmaxf(vmx, pv.y);
+                    }
+                } else
                 for (int bd = 0; bd < a.nb; ++bd) {
                     const int cnt = a.band_cnt[bd];                     // 1 <= band_n <= band_cnt is guaranteed by the plan (syg_api.cu)
                     float2 pv = make_float2(__uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u));   // empty band: mean of nothing -> NaN (numpy)
-                    if (cnt > 0) pv = band_peak_valley_stream(pp, a.band_lo[bd], cnt, a.band_n[bd]);
+                    if (cnt > 0) pv = band_peak_valley_stream<false>(pp, a.band_lo[bd], cnt, a.band_n[bd]);
                     mine_pv = (lane == bd) ? pv.x : mine_pv;
                     mine_pv = (lane_v == bd) ? pv.y : mine_pv;
                     pmx = fmaxf(pmx, pv.x);                             // fmaxf drops the NaN of an empty band

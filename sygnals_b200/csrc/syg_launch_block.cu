@@ -13,7 +13,7 @@ static int frame_block_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st,
     static KernelCache kc;
     auto kfn = sygdev::frame_kernel<TL, MODE>;
     int blocks_per_sm = 0;
-    if (int rc = prepare_kernel(kfn, sygdev::kThreads, SM::bytes, 0, kc, &blocks_per_sm, err)) return rc;
+    if (int rc = prepare_kernel(kfn, sygdev::kThreads, SM::bytes, kc, &blocks_per_sm, err)) return rc;
     const long long n_rounds = (a.n_frames + TL::F - 1) / TL::F;
     if (n_rounds <= 0) return 0;
     const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * blocks_per_sm);
@@ -27,9 +27,9 @@ static int stft_tile_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, s
     using SM = sygdev::StftTileSmem<TL, TT>;
     auto kfn = sygdev::stft_tile_kernel<TL, TT>;
     const size_t smem = SM::bytes(a.out_kind == 0);
-    static KernelCache kc[2];                                       // occupancy differs between the float and the complex tile
+    static KernelCache kc;
     int blocks_per_sm = 0;
-    if (int rc = prepare_kernel(kfn, sygdev::kThreads, smem, SM::bytes(true), kc[a.out_kind == 0], &blocks_per_sm, err)) return rc;
+    if (int rc = prepare_kernel(kfn, sygdev::kThreads, smem, kc, &blocks_per_sm, err)) return rc;
     const long long n_tiles = (a.n_frames + TT - 1) / TT;
     if (n_tiles <= 0) return 0;
     const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * blocks_per_sm);
@@ -72,7 +72,7 @@ int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_
     if (smem > 48 * 1024) {                         // the S_db tile exceeds the default 48 KB for wide mel banks
         static KernelCache kc;
         int nb = 0;
-        if (int rc = prepare_kernel(sygdev::finalize_kernel, sygdev::kThreads, smem, 0, kc, &nb, err)) return rc;
+        if (int rc = prepare_kernel(sygdev::finalize_kernel, sygdev::kThreads, smem, kc, &nb, err)) return rc;
     }
     SYG_LAUNCH(sygdev::finalize_kernel, dim3(grid_x, grid_y), dim3(sygdev::kThreads), smem, st, a);
     LCK(cudaGetLastError());

@@ -13,7 +13,7 @@ static int welch_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::
     static KernelCache kc;
     auto kfn = sygdev::welch_kernel<TL>;
     int blocks_per_sm = 0;
-    if (int rc = prepare_kernel(kfn, sygdev::kThreads, SM::bytes, 0, kc, &blocks_per_sm, err)) return rc;
+    if (int rc = prepare_kernel(kfn, sygdev::kThreads, SM::bytes, kc, &blocks_per_sm, err)) return rc;
     if (a.g.n_units <= 0) return 0;
     const int grid = (int)std::min<long long>(a.g.n_units, (long long)sm_count * blocks_per_sm);
     SYG_LAUNCH(kfn, grid, sygdev::kThreads, SM::bytes, st, a);
@@ -27,7 +27,7 @@ static int welch_warp_t(const syg::WelchArgs& a, int sm_count, cudaStream_t st, 
     static KernelCache kc;
     auto kfn = sygdev::welch_warp_kernel<TL, NT, MINB, TBLW>;
     int blocks_per_sm = 0;
-    if (int rc = prepare_kernel(kfn, NT, WW::bytes, 0, kc, &blocks_per_sm, err)) return rc;
+    if (int rc = prepare_kernel(kfn, NT, WW::bytes, kc, &blocks_per_sm, err)) return rc;
     if (a.g.n_units <= 0) return 0;
     const long long want = (a.g.n_units + NT / 32 - 1) / (NT / 32);
     const int grid = (int)std::min<long long>(want, (long long)sm_count * blocks_per_sm);
