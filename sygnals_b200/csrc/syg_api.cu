@@ -190,8 +190,12 @@ int get_window(syg_ctx* ctx, int window, int win_length, int n_fft, bool centred
 // failures as a negative SYG_E_* code plus a message.
 int launch_rc(int rc, const std::string& err) { return rc == SYG_OK ? SYG_OK : fail(rc, "%s", err.c_str()); }
 
-int launch_features(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
+int launch_features(int n_fft, const syg::FrameArgs& a_in, int sm_count, cudaStream_t st) {
     std::string err;
+    static int variant = -1;
+    if (variant < 0) { const char* e = std::getenv("SYGB200_VARIANT"); variant = e ? std::atoi(e) : 0; }
+    syg::FrameArgs a = a_in;
+    a.variant = variant;
     if (n_fft > 2048) return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_FEATURES, a, sm_count, st, err), err);
     constexpr unsigned extra = syg::FB_BANDWIDTH | syg::FB_FLATNESS | syg::FB_DOMINANT | syg::FB_MEAN_AMP | syg::FB_STD_AMP;
     return launch_rc(syglaunch::frame_warp(n_fft, (a.mask & extra) != 0, a, sm_count, st, err), err);

@@ -82,6 +82,7 @@ struct FrameArgs {
     int mel_pw_f4;              // float4 count of mel_pw (for the shared-memory copy of the plan tables)
     int mel_nsweeps;            // sweeps of the warp kernel's mel plan and their float4 step counts (host side: lets the launcher
     int mel_steps[8];           // pick a plan-specialised kernel); 0 sweeps = not recorded
+    int variant;                // measurement switch (SYGB200_VARIANT, default 0): bit 0 = per-scheduler lock step (see frame_warp_kernel)
     // ---- stft
     int out_kind;               // 0 complex64, 1 magnitude, 2 power
     void* stft_out;             // [n_units][B][T]
