@@ -122,8 +122,8 @@ void syg_ctx_destroy(syg_ctx* ctx);
 int syg_ctx_set_workspace_limit(syg_ctx* ctx, size_t bytes);
 int syg_ctx_sm_count(const syg_ctx* ctx);
 /* optional per-kernel timing for bench.py: CUDA events around every kernel launch on the launching stream.
- * read: ms[3] / launches[3] = {frame kernel (FFT + features or STFT), finalize kernel, welch kernel}, summed
- * since the last reset; synchronises on the recorded events. */
+ * read: ms[4] / launches[4] = {frame kernel (FFT + features or STFT), finalize kernel, welch kernel, other (ingest +
+ * aggregation)}, summed since the last reset; synchronises on the recorded events. */
 int syg_ctx_profile_enable(syg_ctx* ctx, int on);
 int syg_ctx_profile_read(syg_ctx* ctx, double* ms, int64_t* launches, int reset);
 
@@ -146,6 +146,30 @@ int syg_features_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* un
 int syg_features_host_pcm16(syg_ctx* ctx, const int16_t* y_host, const syg_units* units, const syg_feature_params* p,
                             float* out_host);
 int syg_pcm16_to_f32(syg_ctx* ctx, const int16_t* in_dev, float* out_dev, int64_t n, void* stream);
+
+/* General ingest = load_audio(file, sr=None, mono=True) (sygnals/core/audio/io.py:38-102 -> librosa.load -> soundfile.read(dtype=
+ * float32) + librosa.to_mono) for the payload of a WAV 'data' chunk: `n_frames` interleaved frames of `channels` samples.
+ * Normalisation as libsndfile: u8 (x-128)/128, s16 x/2^15, s24 x/2^23 (little endian), s32 x/2^31, f32 unchanged; channel mean as
+ * numpy's np.mean(axis=0) on float32 (sequential float32 sum, one division).  Bit-exact against that arithmetic.
+ * The header is parsed on the host (sygnals_b200/core/audio/io.py); resampling (sr != native) stays on the reference path. */
+enum { SYG_PCM_U8 = 0, SYG_PCM_S16 = 1, SYG_PCM_S24 = 2, SYG_PCM_S32 = 3, SYG_PCM_F32 = 4 };
+int syg_ingest_pcm(syg_ctx* ctx, const void* raw_dev, int32_t sample_format, int32_t channels, int64_t n_frames,
+                   float* mono_dev, void* stream);
+/* syg_features_host_f32 for a PCM payload in host memory: the raw bytes cross PCIe, ingest runs on the device.  `units` counts
+ * FRAMES of the payload (one frame = `channels` samples = one mono sample after the mix-down). */
+int syg_features_host_pcm(syg_ctx* ctx, const void* raw_host, int32_t sample_format, int32_t channels, const syg_units* units,
+                          const syg_feature_params* p, float* out_host);
+
+/* Segment vectors: extract_features() per unit followed by format_feature_vectors_per_segment() (sygnals/core/ml_utils/
+ * formatters.py:51-163, the consumer in `sygnals save dataset`, sygnals/cli/save_cmd.py:140-190) with every unit as one segment:
+ * out [n_units][n_rows] float64, agg[r] in SYG_AGG_* per feature row (host array).  The frame features [n_units][n_rows][T] stay
+ * in a library-owned block on the device: the result that crosses PCIe (host forms) or NVLink (the final gather) is T times smaller. */
+int syg_segment_vectors_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, const syg_feature_params* p,
+                            const int32_t* agg, double* out_dev, void* stream);
+int syg_segment_vectors_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, const syg_feature_params* p,
+                                 const int32_t* agg, double* out_host);
+int syg_segment_vectors_host_pcm(syg_ctx* ctx, const void* raw_host, int32_t sample_format, int32_t channels,
+                                 const syg_units* units, const syg_feature_params* p, const int32_t* agg, double* out_host);
 
 /* compute_stft(): out [n_units][1 + n_fft/2][T]; complex64 (interleaved) / float32 magnitude / float32 power */
 int syg_stft_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, int32_t n_fft, int32_t hop_length,

@@ -526,3 +526,45 @@ def format_feature_vectors_per_segment(features_dict, segment_indices, aggregati
         for j, n in enumerate(names):
             out[i, j] = funcs[n](np.asarray(features_dict[n], dtype=np.float64)[s:e])
     return out
+
+
+# ------------------------------------------------------------------------------------------------ audio ingest
+# sygnals/core/audio/io.py:38-102 load_audio -> librosa.load(path, sr=None, mono=True) -> soundfile.read(dtype='float32',
+# always_2d=False).T -> librosa.to_mono (np.mean(y, axis=0)) -> .astype(float64) (io.py:94-95).  soundfile / libsndfile are
+# third-party (python-soundfile >= 0.12 over libsndfile 1.x; not vendored under /root/reference, not installable offline): the
+# integer -> float normalisation below restates libsndfile's published behaviour for float reads of PCM files
+# (src/pcm.c: u8 (x - 128) / 128, s16 x / 0x8000, s24 and s32 as 32-bit words / 0x80000000); the mix-down is numpy itself.
+PCM_U8, PCM_S16, PCM_S24, PCM_S32, PCM_F32 = 0, 1, 2, 3, 4
+
+
+def pcm_payload_to_float32(raw, fmt: int, channels: int) -> np.ndarray:
+    """Bytes of a WAV data chunk -> float32 [frames, channels] as soundfile.read(dtype='float32', always_2d=True) returns them."""
+    raw = np.frombuffer(bytes(raw), dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw.view(np.uint8).reshape(-1)
+    bps = {PCM_U8: 1, PCM_S16: 2, PCM_S24: 3, PCM_S32: 4, PCM_F32: 4}[fmt]
+    frames = raw.size // (bps * channels)
+    raw = raw[: frames * bps * channels]
+    if fmt == PCM_U8:
+        x = (raw.astype(np.int32) - 128).astype(np.float32) * np.float32(1.0 / 128.0)
+    elif fmt == PCM_S16:
+        x = raw.view("<i2").astype(np.float32) * np.float32(1.0 / 32768.0)
+    elif fmt == PCM_S24:
+        b = raw.reshape(-1, 3).astype(np.int32)
+        w = (b[:, 0] << 8) | (b[:, 1] << 16) | (b[:, 2] << 24)                  # libsndfile: the sample in the top 24 bits of an int32
+        x = w.astype(np.int32).astype(np.float32) * np.float32(1.0 / 2147483648.0)
+    elif fmt == PCM_S32:
+        x = raw.view("<i4").astype(np.float32) * np.float32(1.0 / 2147483648.0)
+    elif fmt == PCM_F32:
+        x = raw.view("<f4").copy()
+    else:
+        raise ValueError(fmt)
+    return x.reshape(frames, channels)
+
+
+def load_audio_payload(raw, fmt: int, channels: int, mono: bool = True) -> np.ndarray:
+    """load_audio(...)[0] for a WAV payload: float64, (n,) if mono else (channels, n)."""
+    y = pcm_payload_to_float32(raw, fmt, channels).T                              # librosa.load: y = sf_desc.read(...).T
+    if mono and y.shape[0] > 1:
+        y = np.mean(y, axis=0)                                                    # librosa.to_mono
+    elif y.shape[0] == 1:
+        y = y[0]
+    return y.astype(np.float64)

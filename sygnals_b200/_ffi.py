@@ -41,6 +41,8 @@ PAD_IDS = {"constant": 0, "reflect": 1}
 OUT_COMPLEX, OUT_MAGNITUDE, OUT_POWER = 0, 1, 2
 SCALING_IDS = {"density": 0, "spectrum": 1}
 AGG_IDS = {"mean": 0, "std": 1, "median": 2, "min": 3, "max": 4}      # formatters.py:39-45
+PCM_U8, PCM_S16, PCM_S24, PCM_S32, PCM_F32 = 0, 1, 2, 3, 4              # sample formats of a WAV 'data' payload
+PCM_BYTES = {PCM_U8: 1, PCM_S16: 2, PCM_S24: 3, PCM_S32: 4, PCM_F32: 4}
 MAX_FEATURES = 16
 
 
@@ -96,6 +98,11 @@ class Library:
             "syg_features_host_f32": (C.c_int, [vp, vp, PU, PP, vp]),
             "syg_features_host_pcm16": (C.c_int, [vp, vp, PU, PP, vp]),
             "syg_pcm16_to_f32": (C.c_int, [vp, vp, vp, i64, vp]),
+            "syg_ingest_pcm": (C.c_int, [vp, vp, i32, i32, i64, vp, vp]),
+            "syg_features_host_pcm": (C.c_int, [vp, vp, i32, i32, PU, PP, vp]),
+            "syg_segment_vectors_f32": (C.c_int, [vp, vp, PU, PP, vp, vp, vp]),
+            "syg_segment_vectors_host_f32": (C.c_int, [vp, vp, PU, PP, vp, vp]),
+            "syg_segment_vectors_host_pcm": (C.c_int, [vp, vp, i32, i32, PU, PP, vp, vp]),
             "syg_stft_f32": (C.c_int, [vp, vp, PU, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
             "syg_stft_host_f32": (C.c_int, [vp, vp, PU, i32, i32, i32, i32, i32, i32, i32, vp]),
             "syg_psd_welch_f32": (C.c_int, [vp, vp, PU, f64, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
@@ -277,11 +284,12 @@ class Engine:
         self.lib.check(self.lib.dll.syg_ctx_profile_enable(self._h, int(on)))
 
     def profile_read(self, reset: bool = True) -> dict:
-        """{'frame': (ms, launches), 'finalize': (...), 'welch': (...)} summed since the last reset."""
-        ms = (C.c_double * 3)()
-        n = (C.c_int64 * 3)()
+        """{'frame': (ms, launches), 'finalize': (...), 'welch': (...), 'other': (...)} summed since the last reset
+        ('other' = ingest + aggregation kernels)."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
         self.lib.check(self.lib.dll.syg_ctx_profile_read(self._h, C.addressof(ms), C.addressof(n), int(reset)))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("frame", "finalize", "welch"))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("frame", "finalize", "welch", "other"))}
 
     # ------------------------------------------------------------------ geometry helpers
     @staticmethod
@@ -331,6 +339,46 @@ class Engine:
         self.lib.check(self.lib.dll.syg_features_host_pcm16(self._h, y_ptr, C.byref(units), C.byref(p), out.ctypes.data))
         return out
 
+    def features_host_pcm(self, raw_ptr: int, fmt: int, channels: int, units: SygUnits, p: SygFeatureParams,
+                          out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``features_host`` for an interleaved PCM payload in host memory (``units`` count frames of the payload)."""
+        rows = self.rows(p)
+        T = self.frame_count(units.unit_len, p.frame_length, p.hop_length, p.center)
+        if out is None:
+            out = np.empty((units.n_units, rows, T), dtype=np.float32)
+        self.lib.check(self.lib.dll.syg_features_host_pcm(self._h, raw_ptr, int(fmt), int(channels), C.byref(units), C.byref(p),
+                                                          out.ctypes.data))
+        return out
+
+    def segment_vectors_host(self, y_ptr: int, units: SygUnits, p: SygFeatureParams, agg_ids: Sequence[int],
+                             out: Optional[np.ndarray] = None, fmt: Optional[int] = None, channels: int = 1) -> np.ndarray:
+        """float64 ``[n_units, n_rows]``: per-unit features aggregated over the unit's frames on the device (formatters.py:51-163).
+        ``fmt=None``: ``y_ptr`` points at float32 mono samples; else at an interleaved PCM payload of format ``fmt``."""
+        rows = self.rows(p)
+        if len(agg_ids) != rows:
+            raise ValueError("one aggregation id per feature row")
+        if out is None:
+            out = np.empty((units.n_units, rows), dtype=np.float64)
+        agg = (C.c_int32 * max(1, rows))(*[int(a) for a in agg_ids])
+        if fmt is None:
+            rc = self.lib.dll.syg_segment_vectors_host_f32(self._h, y_ptr, C.byref(units), C.byref(p), C.addressof(agg), out.ctypes.data)
+        else:
+            rc = self.lib.dll.syg_segment_vectors_host_pcm(self._h, y_ptr, int(fmt), int(channels), C.byref(units), C.byref(p),
+                                                           C.addressof(agg), out.ctypes.data)
+        self.lib.check(rc)
+        return out
+
+    def segment_vectors_dev(self, y_ptr: int, units: SygUnits, p: SygFeatureParams, agg_ids: Sequence[int], out_ptr: int,
+                            stream: int = 0) -> None:
+        """Device form: float32 samples in HBM -> float64 ``[n_units, n_rows]`` in HBM, asynchronous on ``stream``."""
+        agg = (C.c_int32 * max(1, len(agg_ids)))(*[int(a) for a in agg_ids])
+        self.lib.check(self.lib.dll.syg_segment_vectors_f32(self._h, y_ptr, C.byref(units), C.byref(p), C.addressof(agg), out_ptr,
+                                                            stream or None))
+
+    def ingest_pcm_dev(self, raw_ptr: int, fmt: int, channels: int, n_frames: int, out_ptr: int, stream: int = 0) -> None:
+        """Interleaved PCM in HBM -> mono float32 in HBM (load_audio(mono=True) arithmetic)."""
+        self.lib.check(self.lib.dll.syg_ingest_pcm(self._h, raw_ptr, int(fmt), int(channels), int(n_frames), out_ptr, stream or None))
+
     def stft_host(self, y: np.ndarray, units: SygUnits, n_fft: int, hop: int, win_length: int, window: int = 0,
                   center: bool = True, pad_mode: int = 0, out_kind: int = OUT_COMPLEX) -> np.ndarray:
         y = _f32c(y)
@@ -379,30 +427,19 @@ class Engine:
 
     # ------------------------------------------------------------------ pinned host memory
     def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:
-        """numpy array backed by cudaHostAlloc memory (freed when the array is garbage collected)."""
+        """numpy array backed by cudaHostAlloc memory; the block is released when the array (and every view of it) is collected."""
+        import weakref
         dtype = np.dtype(dtype)
-        n = int(np.prod(shape)) * dtype.itemsize
+        count = int(np.prod(shape))
+        n = count * dtype.itemsize
         p = C.c_void_p()
         self.lib.check(self.lib.dll.syg_host_alloc(C.byref(p), max(n, 1)))
         buf = (C.c_char * max(n, 1)).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        lib = self.lib
-
-        class _Owner:
-            def __init__(self, ptr):
-                self.ptr = ptr
-
-            def __del__(self):
-                try:
-                    lib.dll.syg_host_free(self.ptr)
-                except Exception:
-                    pass
-
-        _owners[id(buf)] = (buf, _Owner(p))
-        return arr
+        # views keep `buf` alive through .base; when the last one dies the finalizer frees the page-locked block
+        weakref.finalize(buf, self.lib.dll.syg_host_free, C.c_void_p(p.value))
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
-_owners: dict = {}
 _engines: dict = {}
 _engine_lock = threading.Lock()
 

@@ -99,9 +99,9 @@ def segment_features(y, sr: int, segment_length_sec: float, features: Sequence[s
         units = eng.units_table(starts.ctypes.data, valid.ctypes.data, n, seg_len, total)
         keep = (starts, valid)
     out = _run(y, units, n, p, eng)
-    if keep is not None and _is_torch(y):
-        import torch
-        torch.cuda.current_stream(y.device).synchronize()       # the table tensors must outlive the launch
+    # `keep` (device tables) may be dropped without a host synchronisation: the kernels are queued on the current torch stream and
+    # the caching allocator reuses a freed block only for work queued later on that stream
+    del keep
     return {"names": feature_row_names(features, feature_params), "features": out, "starts": starts, "valid": valid,
             "seg_len": seg_len, "seg_hop": seg_hop}
 

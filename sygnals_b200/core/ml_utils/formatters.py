@@ -60,7 +60,7 @@ def aggregate_segments(features, names: Sequence[str], aggregation: Union[str, D
             off = torch.arange(n, device=f.device, dtype=torch.int64) * (rows * T) + r0 * T
             eng.aggregate_dev(f.data_ptr(), n, r1 - r0, T, ids[r0:r1], part.data_ptr(), seg_off_ptr=off.data_ptr(), fixed_len=T,
                               stream=torch.cuda.current_stream(f.device).cuda_stream)
-            torch.cuda.current_stream(f.device).synchronize()  # `off` must outlive the launch
+            del off                                            # stream-ordered allocator: safe to drop once the launch is queued
             if part is not out:
                 out[:, r0:r1] = part
     return out

@@ -75,9 +75,39 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct PinnedBuf {                 // page-locked host staging owned by a lane (cudaMemcpyAsync from it never stalls the stream)
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SYG_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = (bytes + 4095) / 4096 * 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { p = nullptr; return fail(SYG_E_NOMEM, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return SYG_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct Lane {                      // one in-flight chunk of a *_host_* call
     cudaStream_t stream = nullptr;
-    DevBuf in, in16, out0, out1, starts, valid, ws;
+    DevBuf in, raw, out0, out1, starts, valid, ws, feat;
+    PinnedBuf tbl;                 // explicit unit tables of the chunk (starts | valid), reused once tbl_done has passed
+    cudaEvent_t tbl_done = nullptr;
+    bool tbl_used = false;
+};
+
+// what a *_host_* call is handed: float32 mono samples (fmt < 0) or an interleaved PCM payload (SYG_PCM_*, `channels` per frame)
+struct InFmt {
+    int fmt = -1, channels = 1;
+    size_t frame_bytes() const {
+        if (fmt < 0) return sizeof(float);
+        const size_t bps = fmt == SYG_PCM_U8 ? 1 : (fmt == SYG_PCM_S16 ? 2 : (fmt == SYG_PCM_S24 ? 3 : 4));
+        return bps * (size_t)channels;
+    }
 };
 
 }  // namespace
@@ -96,12 +126,12 @@ struct syg_ctx {
     bool prof_on = false;
     struct ProfPair { cudaEvent_t a, b; int kind; };
     std::vector<ProfPair> prof_pairs;
-    double prof_ms[3] = {0, 0, 0};
-    long long prof_n[3] = {0, 0, 0};
+    double prof_ms[4] = {0, 0, 0, 0};
+    long long prof_n[4] = {0, 0, 0, 0};
 };
 
 namespace {
-enum { PROF_FRAME = 0, PROF_FINALIZE = 1, PROF_WELCH = 2 };
+enum { PROF_FRAME = 0, PROF_FINALIZE = 1, PROF_WELCH = 2, PROF_OTHER = 3 };   // other = ingest + aggregation
 struct ProfScope {
     syg_ctx* c; cudaStream_t st; int kind; cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(syg_ctx* c_, cudaStream_t st_, int kind_) : c(c_), st(st_), kind(kind_) {
@@ -260,8 +290,14 @@ int rows_of(const syg_feature_params* p, int32_t* n_rows) {
         if (f < 0 || f >= SYG_FEAT_COUNT_) return fail(SYG_E_BADARG, "unknown feature id %d", f);
         if (seen & (1u << f)) return fail(SYG_E_BADARG, "feature id %d requested twice", f);
         seen |= 1u << f;
-        if (f == SYG_FEAT_MFCC) rows += p->n_mfcc;
-        else if (f == SYG_FEAT_SPECTRAL_CONTRAST) rows += p->contrast_n_bands + 1;
+        if (f == SYG_FEAT_MFCC) {
+            if (p->n_mfcc < 1 || p->n_mfcc > 256) return fail(SYG_E_BADARG, "n_mfcc=%d out of range [1, 256]", p->n_mfcc);
+            rows += p->n_mfcc;
+        } else if (f == SYG_FEAT_SPECTRAL_CONTRAST) {
+            if (p->contrast_n_bands < 1 || p->contrast_n_bands > syg::kMaxBands - 1)
+                return fail(SYG_E_BADARG, "n_bands=%d out of range [1, %d]", p->contrast_n_bands, syg::kMaxBands - 1);
+            rows += p->contrast_n_bands + 1;
+        }
         else rows += 1;
     }
     *n_rows = rows;
@@ -511,10 +547,10 @@ int check_host_units(const syg_units* u) {
 
 // Generic chunked host pipeline: H2D of the chunk's samples, `run` on the lane's stream, D2H of up to two outputs.
 template <class Run>
-int host_pipeline(syg_ctx* ctx, const void* y_host_any, bool pcm16, const syg_units* u, size_t out0_per_unit, void* out0_host,
+int host_pipeline(syg_ctx* ctx, const void* y_host_any, InFmt inf, const syg_units* u, size_t out0_per_unit, void* out0_host,
                   size_t out1_per_unit, void* out1_host, size_t ws_per_unit, long long max_chunk_units, Run run) {
-    const float* y_host = pcm16 ? nullptr : reinterpret_cast<const float*>(y_host_any);
-    const int16_t* y_host16 = pcm16 ? reinterpret_cast<const int16_t*>(y_host_any) : nullptr;
+    const unsigned char* y_bytes = reinterpret_cast<const unsigned char*>(y_host_any);
+    const size_t fb = inf.frame_bytes();
     if (u->n_units == 0) return SYG_OK;
     const size_t in_target = (size_t)128 << 20, out_target = (size_t)256 << 20;
     long long span = u->unit_starts ? u->unit_len : std::max<long long>(1, std::min(u->unit_stride, u->unit_len));
@@ -524,11 +560,11 @@ int host_pipeline(syg_ctx* ctx, const void* y_host_any, bool pcm16, const syg_un
     chunk = std::min(chunk, max_chunk_units);
     if (u->n_units > 1) chunk = std::min<long long>(chunk, (u->n_units + 1) / 2);           // keep both lanes busy
     chunk = std::max<long long>(chunk, 1);
-    for (int l = 0; l < 2; ++l)
+    for (int l = 0; l < 2; ++l) {
         if (!ctx->lanes[l].stream) CK(cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking));
+        if (!ctx->lanes[l].tbl_done) CK(cudaEventCreateWithFlags(&ctx->lanes[l].tbl_done, cudaEventDisableTiming));
+    }
     int li = 0;
-    std::vector<long long> rel;
-    std::vector<int> val;
     for (long long u0 = 0; u0 < u->n_units; u0 += chunk, li ^= 1) {
         const long long n = std::min(chunk, u->n_units - u0);
         Lane& L = ctx->lanes[li];
@@ -539,15 +575,14 @@ int host_pipeline(syg_ctx* ctx, const void* y_host_any, bool pcm16, const syg_un
         if ((rc = L.out0.ensure(std::max<size_t>(out0_per_unit * n, 256)))) return rc;
         if (out1_per_unit && (rc = L.out1.ensure(out1_per_unit * n))) return rc;
         if (ws_per_unit && (rc = L.ws.ensure(ws_per_unit * n + 4096))) return rc;
-        // the lane's previous chunk must have left its buffers (same stream => ordered); host-side staging
-        // vectors are reused, so wait for the previous upload of this lane's tables
-        if (e > b && !pcm16) CK(cudaMemcpyAsync(L.in.p, y_host + b, (size_t)(e - b) * sizeof(float), cudaMemcpyHostToDevice, L.stream));
-        if (e > b && pcm16) {                                           // half the PCIe bytes; widened to float32 on the device
-            if ((rc = L.in16.ensure((size_t)(e - b) * sizeof(int16_t)))) return rc;
-            CK(cudaMemcpyAsync(L.in16.p, y_host16 + b, (size_t)(e - b) * sizeof(int16_t), cudaMemcpyHostToDevice, L.stream));
+        // the lane's previous chunk has left its device buffers when this chunk's work reaches them (same stream => ordered)
+        if (e > b && inf.fmt < 0) CK(cudaMemcpyAsync(L.in.p, y_bytes + (size_t)b * fb, (size_t)(e - b) * fb, cudaMemcpyHostToDevice, L.stream));
+        if (e > b && inf.fmt >= 0) {                                    // PCM payload: fewer PCIe bytes; de-interleaved, averaged and widened on the device
+            if ((rc = L.raw.ensure((size_t)(e - b) * fb))) return rc;
+            CK(cudaMemcpyAsync(L.raw.p, y_bytes + (size_t)b * fb, (size_t)(e - b) * fb, cudaMemcpyHostToDevice, L.stream));
             std::string err;
-            const int crc = syglaunch::pcm16_to_f32(reinterpret_cast<const short*>(L.in16.p), reinterpret_cast<float*>(L.in.p), e - b,
-                                                    ctx->sm_count, L.stream, err);
+            ProfScope ps(ctx, L.stream, PROF_OTHER);
+            const int crc = syglaunch::pcm_to_f32(L.raw.p, inf.fmt, inf.channels, e - b, reinterpret_cast<float*>(L.in.p), ctx->sm_count, L.stream, err);
             if (crc) return fail(crc, "%s", err.c_str());
         }
         syg_units cu;
@@ -560,8 +595,13 @@ int host_pipeline(syg_ctx* ctx, const void* y_host_any, bool pcm16, const syg_un
             cu.unit_stride = u->unit_stride;
             cu.total_len = e - b;
         } else {
-            rel.resize(n);
-            val.resize(n);
+            // the chunk's table goes through the lane's own pinned staging block; it is rewritten only after the copy that read it
+            // two chunks ago has completed (an event wait that has practically always passed), so the streams never stall
+            const size_t off_valid = ((size_t)n * sizeof(long long) + 15) / 16 * 16;
+            if (L.tbl_used) CK(cudaEventSynchronize(L.tbl_done));
+            if ((rc = L.tbl.ensure(off_valid + (size_t)n * sizeof(int)))) return rc;
+            long long* rel = reinterpret_cast<long long*>(L.tbl.p);
+            int* val = reinterpret_cast<int*>(reinterpret_cast<char*>(L.tbl.p) + off_valid);
             for (long long i = 0; i < n; ++i) {
                 const long long s = u->unit_starts[u0 + i];
                 long long v = u->unit_valid ? u->unit_valid[u0 + i] : u->total_len - s;
@@ -571,9 +611,10 @@ int host_pipeline(syg_ctx* ctx, const void* y_host_any, bool pcm16, const syg_un
             }
             if ((rc = L.starts.ensure(n * sizeof(long long)))) return rc;
             if ((rc = L.valid.ensure(n * sizeof(int)))) return rc;
-            CK(cudaMemcpyAsync(L.starts.p, rel.data(), n * sizeof(long long), cudaMemcpyHostToDevice, L.stream));
-            CK(cudaMemcpyAsync(L.valid.p, val.data(), n * sizeof(int), cudaMemcpyHostToDevice, L.stream));
-            CK(cudaStreamSynchronize(L.stream));                      // rel/val are reused by the next chunk
+            CK(cudaMemcpyAsync(L.starts.p, rel, n * sizeof(long long), cudaMemcpyHostToDevice, L.stream));
+            CK(cudaMemcpyAsync(L.valid.p, val, n * sizeof(int), cudaMemcpyHostToDevice, L.stream));
+            CK(cudaEventRecord(L.tbl_done, L.stream));
+            L.tbl_used = true;
             cu.unit_stride = 0;
             cu.total_len = e - b;
             cu.unit_starts = reinterpret_cast<const int64_t*>(L.starts.p);
@@ -707,7 +748,9 @@ void syg_ctx_destroy(syg_ctx* ctx) {
     ctx->ws.release();
     if (ctx->ws_done) cudaEventDestroy(ctx->ws_done);
     for (auto& l : ctx->lanes) {
-        l.in.release(); l.in16.release(); l.out0.release(); l.out1.release(); l.starts.release(); l.valid.release(); l.ws.release();
+        l.in.release(); l.raw.release(); l.out0.release(); l.out1.release(); l.starts.release(); l.valid.release(); l.ws.release(); l.feat.release();
+        l.tbl.release();
+        if (l.tbl_done) cudaEventDestroy(l.tbl_done);
         if (l.stream) cudaStreamDestroy(l.stream);
     }
     delete ctx;
@@ -744,7 +787,7 @@ int syg_ctx_profile_read(syg_ctx* ctx, double* ms, int64_t* launches, int reset)
         cudaEventDestroy(pp.b);
     }
     ctx->prof_pairs.clear();
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         if (ms) ms[i] = ctx->prof_ms[i];
         if (launches) launches[i] = ctx->prof_n[i];
         if (reset) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
@@ -816,9 +859,12 @@ int syg_features_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, c
     return SYG_OK;
 }
 
-static int features_host_impl(syg_ctx* ctx, const void* y_host, bool pcm16, const syg_units* units, const syg_feature_params* p,
-                              float* out_host) {
+// agg == nullptr: out_host is float32 [n_units][n_rows][T];  else: float64 [n_units][n_rows] (per-row SYG_AGG_* over the frames)
+static int features_host_impl(syg_ctx* ctx, const void* y_host, InFmt inf, const syg_units* units, const syg_feature_params* p,
+                              const int32_t* agg, void* out_host) {
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    if (inf.fmt >= 0 && (inf.fmt > SYG_PCM_F32 || inf.channels < 1 || inf.channels > 64))
+        return fail(SYG_E_BADARG, "bad PCM layout (format %d, %d channels)", inf.fmt, inf.channels);
     int rc = check_host_units(units);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -828,26 +874,114 @@ static int features_host_impl(syg_ctx* ctx, const void* y_host, bool pcm16, cons
     if (units->n_units == 0 || pl.T <= 0 || pl.n_rows == 0) return SYG_OK;
     if (!y_host && units->total_len > 0) return fail(SYG_E_BADARG, "y_host is NULL");
     if (!out_host) return fail(SYG_E_BADARG, "out_host is NULL");
-    const size_t out_per_unit = (size_t)pl.n_rows * pl.T * sizeof(float);
+    if (agg) {
+        if (pl.n_rows > 64) return fail(SYG_E_UNSUPPORTED, "aggregation supports at most 64 rows per call");
+        for (int i = 0; i < pl.n_rows; ++i)
+            if (agg[i] < SYG_AGG_MEAN || agg[i] > SYG_AGG_MAX) return fail(SYG_E_BADARG, "unknown aggregation id %d", agg[i]);
+    }
+    const size_t feat_per_unit = (size_t)pl.n_rows * pl.T * sizeof(float);
+    const size_t out_per_unit = agg ? (size_t)pl.n_rows * sizeof(double) : feat_per_unit;
     const int n_fft = p->frame_length;
-    return host_pipeline(ctx, y_host, pcm16, units, out_per_unit, out_host, 0, nullptr, features_ws_bytes(pl, 1), 1LL << 40,
+    // aggregated calls keep the [n, rows, T] block on the device: bound the chunk by it (it replaces the D2H-sized output buffer)
+    const long long max_chunk = agg ? std::max<long long>(1, (long long)(((size_t)256 << 20) / feat_per_unit)) : (1LL << 40);
+    return host_pipeline(ctx, y_host, inf, units, out_per_unit, out_host, 0, nullptr, features_ws_bytes(pl, 1), max_chunk,
                          [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long n) -> int {
                              int r = L.ws.ensure(features_ws_bytes(pl, n));
                              if (r) return r;
+                             float* feat = reinterpret_cast<float*>(L.out0.p);
+                             if (agg) {
+                                 if ((r = L.feat.ensure(feat_per_unit * n))) return r;
+                                 feat = reinterpret_cast<float*>(L.feat.p);
+                             }
                              syg::UnitGeom g = chunk_geom(cu, shift);
-                             return run_features_chunk(ctx, pl, y_dev + shift, g, reinterpret_cast<float*>(L.out0.p), L.ws.p,
-                                                       n_fft, L.stream);
+                             r = run_features_chunk(ctx, pl, y_dev + shift, g, feat, L.ws.p, n_fft, L.stream);
+                             if (r || !agg) return r;
+                             std::string err;
+                             ProfScope ps(ctx, L.stream, PROF_OTHER);
+                             const int arc = syglaunch::aggregate(feat, n, pl.n_rows, pl.T, nullptr, nullptr, pl.T, agg,
+                                                                  reinterpret_cast<double*>(L.out0.p), ctx->sm_count, L.stream, err);
+                             return arc ? fail(arc, "%s", err.c_str()) : SYG_OK;
                          });
 }
 
 int syg_features_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, const syg_feature_params* p,
                           float* out_host) {
-    return features_host_impl(ctx, y_host, false, units, p, out_host);
+    return features_host_impl(ctx, y_host, InFmt{}, units, p, nullptr, out_host);
 }
 
 int syg_features_host_pcm16(syg_ctx* ctx, const int16_t* y_host, const syg_units* units, const syg_feature_params* p,
                             float* out_host) {
-    return features_host_impl(ctx, y_host, true, units, p, out_host);
+    return features_host_impl(ctx, y_host, InFmt{SYG_PCM_S16, 1}, units, p, nullptr, out_host);
+}
+
+int syg_features_host_pcm(syg_ctx* ctx, const void* raw_host, int32_t sample_format, int32_t channels, const syg_units* units,
+                          const syg_feature_params* p, float* out_host) {
+    return features_host_impl(ctx, raw_host, InFmt{sample_format, channels}, units, p, nullptr, out_host);
+}
+
+int syg_segment_vectors_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, const syg_feature_params* p,
+                                 const int32_t* agg, double* out_host) {
+    if (!agg) return fail(SYG_E_BADARG, "agg is NULL");
+    return features_host_impl(ctx, y_host, InFmt{}, units, p, agg, out_host);
+}
+
+int syg_segment_vectors_host_pcm(syg_ctx* ctx, const void* raw_host, int32_t sample_format, int32_t channels,
+                                 const syg_units* units, const syg_feature_params* p, const int32_t* agg, double* out_host) {
+    if (!agg) return fail(SYG_E_BADARG, "agg is NULL");
+    return features_host_impl(ctx, raw_host, InFmt{sample_format, channels}, units, p, agg, out_host);
+}
+
+int syg_segment_vectors_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, const syg_feature_params* p,
+                            const int32_t* agg, double* out_dev, void* stream) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    if (!agg) return fail(SYG_E_BADARG, "agg is NULL");
+    int rc = check_units(units);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ENTER_DEVICE(ctx);
+    FeaturePlan pl;
+    if ((rc = build_feature_plan(ctx, units, p, pl))) return rc;
+    if (units->n_units == 0 || pl.T <= 0 || pl.n_rows == 0) return SYG_OK;
+    if (!y_dev && units->total_len > 0) return fail(SYG_E_BADARG, "y_dev is NULL");
+    if (!out_dev) return fail(SYG_E_BADARG, "out_dev is NULL");
+    if (pl.n_rows > 64) return fail(SYG_E_UNSUPPORTED, "aggregation supports at most 64 rows per call");
+    for (int i = 0; i < pl.n_rows; ++i)
+        if (agg[i] < SYG_AGG_MEAN || agg[i] > SYG_AGG_MAX) return fail(SYG_E_BADARG, "unknown aggregation id %d", agg[i]);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // the frame features of a chunk live in a library-owned block behind the workspace: [chunk][rows][T] never reaches the caller
+    const size_t feat_per_unit = (size_t)pl.n_rows * pl.T * sizeof(float);
+    long long chunk = std::max<long long>(1, (long long)(ctx->ws_limit / std::max<size_t>(pl.ws_per_unit + feat_per_unit, 1)));
+    chunk = std::min<long long>(chunk, units->n_units);
+    const size_t ws_bytes = (features_ws_bytes(pl, chunk) + 255) / 256 * 256;
+    if (ctx->ws_done) CK(cudaStreamWaitEvent(st, ctx->ws_done, 0));
+    else CK(cudaEventCreateWithFlags(&ctx->ws_done, cudaEventDisableTiming));
+    if (ws_bytes + feat_per_unit * chunk > ctx->ws.cap) CK(cudaStreamSynchronize(st));
+    if ((rc = ctx->ws.ensure(ws_bytes + feat_per_unit * chunk))) return rc;
+    struct Done { syg_ctx* c; cudaStream_t s; ~Done() { cudaEventRecord(c->ws_done, s); } } done_{ctx, st};
+    float* feat = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->ws.p) + ws_bytes);
+    for (long long u0 = 0; u0 < units->n_units; u0 += chunk) {
+        const long long n = std::min(chunk, units->n_units - u0);
+        syg::UnitGeom g = geom_of(units, u0, n);
+        if ((rc = run_features_chunk(ctx, pl, y_dev, g, feat, ctx->ws.p, p->frame_length, st))) return rc;
+        std::string err;
+        ProfScope ps(ctx, st, PROF_OTHER);
+        const int arc = syglaunch::aggregate(feat, n, pl.n_rows, pl.T, nullptr, nullptr, pl.T, agg, out_dev + (size_t)u0 * pl.n_rows,
+                                             ctx->sm_count, st, err);
+        if (arc) return fail(arc, "%s", err.c_str());
+    }
+    return SYG_OK;
+}
+
+int syg_ingest_pcm(syg_ctx* ctx, const void* raw_dev, int32_t sample_format, int32_t channels, int64_t n_frames, float* mono_dev,
+                   void* stream) {
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    if (n_frames < 0 || (n_frames > 0 && (!raw_dev || !mono_dev))) return fail(SYG_E_BADARG, "bad PCM buffer");
+    if (sample_format < SYG_PCM_U8 || sample_format > SYG_PCM_F32) return fail(SYG_E_BADARG, "unknown PCM sample format %d", sample_format);
+    ENTER_DEVICE(ctx);
+    std::string err;
+    const int rc = syglaunch::pcm_to_f32(raw_dev, sample_format, channels, n_frames, mono_dev, ctx->sm_count,
+                                         reinterpret_cast<cudaStream_t>(stream), err);
+    return rc ? fail(rc, "%s", err.c_str()) : SYG_OK;
 }
 
 int syg_pcm16_to_f32(syg_ctx* ctx, const int16_t* in_dev, float* out_dev, int64_t n, void* stream) {
@@ -898,7 +1032,7 @@ int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units,
     if (!out_host) return fail(SYG_E_BADARG, "out_host is NULL");
     const size_t out_per_unit = (size_t)(n_fft / 2 + 1) * a.T * stft_elem_bytes(out_kind);
     const int sm = ctx->sm_count;
-    return host_pipeline(ctx, y_host, false, units, out_per_unit, out_host, 0, nullptr, 0, 1LL << 40,
+    return host_pipeline(ctx, y_host, InFmt{}, units, out_per_unit, out_host, 0, nullptr, 0, 1LL << 40,
                          [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long n) -> int {
                              syg::FrameArgs c = a;
                              c.y = y_dev + shift;
@@ -944,7 +1078,7 @@ int syg_psd_welch_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* u
     const size_t psd_per_unit = (size_t)(pl.nfft / 2 + 1) * sizeof(float);
     const size_t st_per_unit = stats_host ? 3 * sizeof(float) : 0;
     const int sm = ctx->sm_count;
-    return host_pipeline(ctx, y_host, false, units, psd_per_unit, psd_host, st_per_unit, stats_host, 0, 1LL << 40,
+    return host_pipeline(ctx, y_host, InFmt{}, units, psd_per_unit, psd_host, st_per_unit, stats_host, 0, 1LL << 40,
                          [&](Lane& L, const float* y_dev, const syg_units& cu, long long shift, long long, long long) -> int {
                              syg::WelchArgs c = pl.wa;
                              c.y = y_dev + shift;

@@ -14,6 +14,7 @@ int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_
 int aggregate(const float* feats, long long n_seg, int n_rows, long long row_stride, const long long* seg_off, const int* seg_len,
               int fixed_len, const int* agg_host, double* out, int sm_count, cudaStream_t st, std::string& err);
 int time_extra(const syg::FrameArgs& a, int frame_length, int entropy_bins, int sm_count, cudaStream_t st, std::string& err);
+int pcm_to_f32(const void* raw, int fmt, int channels, long long n_frames, float* out, int sm_count, cudaStream_t st, std::string& err);
 int pcm16_to_f32(const short* in, float* out, long long n, int sm_count, cudaStream_t st, std::string& err);
 int welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err);
 }  // namespace syglaunch

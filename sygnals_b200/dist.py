@@ -74,34 +74,64 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+def _shard_units(eng, plan: ShardPlan, n_have: int, device=None):
+    """Unit description of this rank's block relative to its local sample slice.  Regular grids (the usual case: every start is
+    ``i * seg_hop`` from the slice's first sample) need no table; irregular ones (``min_segment_length_sec`` dropped a segment) go
+    through device / host tables, returned as ``keep`` so the caller holds them for the duration of the call."""
+    n = plan.n_local
+    regular = n == 0 or bool((plan.starts == np.arange(n, dtype=np.int64) * plan.seg_hop).all())
+    if regular:
+        return eng.units_clips(n, plan.seg_len, total_len=n_have, stride=plan.seg_hop), None
+    if device is not None:
+        import torch
+        st = torch.from_numpy(plan.starts).to(device)
+        va = torch.from_numpy(plan.valid).to(device)
+        return eng.units_table(st.data_ptr(), va.data_ptr(), n, plan.seg_len, n_have), (st, va)
+    st, va = np.ascontiguousarray(plan.starts), np.ascontiguousarray(plan.valid)
+    return eng.units_table(st.ctypes.data, va.ctypes.data, n, plan.seg_len, n_have), (st, va)
+
+
 def run_shard(y_local, plan: ShardPlan, sr: int, features: Sequence[str], frame_length: int = 2048, hop_length: int = 512,
               center: bool = True, window: str = "hann", feature_params: Optional[dict] = None,
-              engine: Optional[_ffi.Engine] = None):
+              engine: Optional[_ffi.Engine] = None, aggregation=None, out=None):
     """Features of this rank's segments.  ``y_local`` holds ``y[plan.sample_begin:plan.sample_end]`` (numpy: host path;
-    CUDA torch tensor: device path, asynchronous on the current stream).  Returns float32 ``[n_local, rows, T]``."""
+    CUDA torch tensor: device path, asynchronous on the current stream).  Returns float32 ``[n_local, rows, T]``, or -- with
+    ``aggregation`` ('mean' | 'std' | 'median' | 'min' | 'max' or a per-feature dict: format_feature_vectors_per_segment,
+    formatters.py:51-163, every segment one row) -- float64 ``[n_local, rows]`` straight from the fused device path
+    (``syg_segment_vectors_f32``: the frame features never leave the library's workspace).  ``out``: optional preallocated result."""
     n_have = int(y_local.shape[0])
     if n_have != plan.sample_end - plan.sample_begin:
         raise ValueError(f"y_local has {n_have} samples, the shard needs {plan.sample_end - plan.sample_begin}")
+    ids = None
+    if aggregation is not None:
+        from .core.ml_utils.formatters import _agg_ids
+        ids = _agg_ids(feature_row_names(features, feature_params), aggregation)
     if _is_torch(y_local) and y_local.is_cuda:
         import torch
         eng = engine or _ffi.engine(y_local.device.index or 0)
         p = _ffi.make_params(eng.lib, sr, list(features), frame_length, hop_length, center, window, feature_params)
         rows, T = eng.rows(p), eng.frame_count(plan.seg_len, frame_length, hop_length, center)
-        out = torch.empty((plan.n_local, rows, T), dtype=torch.float32, device=y_local.device)
+        shape = (plan.n_local, rows) if ids is not None else (plan.n_local, rows, T)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float64 if ids is not None else torch.float32, device=y_local.device)
         if out.numel():
-            st = torch.from_numpy(plan.starts).to(y_local.device)
-            va = torch.from_numpy(plan.valid).to(y_local.device)
-            units = eng.units_table(st.data_ptr(), va.data_ptr(), plan.n_local, plan.seg_len, n_have)
+            units, keep = _shard_units(eng, plan, n_have, y_local.device)
             y32 = y_local if (y_local.dtype == torch.float32 and y_local.is_contiguous()) else y_local.contiguous().float()
-            eng.features_dev(y32.data_ptr(), units, p, out.data_ptr(), torch.cuda.current_stream(y_local.device).cuda_stream)
-            torch.cuda.current_stream(y_local.device).synchronize()      # the table tensors must outlive the launch
+            stream = torch.cuda.current_stream(y_local.device).cuda_stream
+            if ids is not None:
+                eng.segment_vectors_dev(y32.data_ptr(), units, p, ids, out.data_ptr(), stream)
+            else:
+                eng.features_dev(y32.data_ptr(), units, p, out.data_ptr(), stream)
+            # `keep` / `y32` may be released now: the kernels are queued on the CURRENT torch stream and the caching allocator hands
+            # a freed block only to work queued later on that same stream, so no host synchronisation is needed here
+            del keep
         return out
     eng = engine or _ffi.engine()
     p = _ffi.make_params(eng.lib, sr, list(features), frame_length, hop_length, center, window, feature_params)
     y32 = np.ascontiguousarray(y_local, dtype=np.float32)
-    starts = np.ascontiguousarray(plan.starts)
-    valid = np.ascontiguousarray(plan.valid)
-    units = eng.units_table(starts.ctypes.data, valid.ctypes.data, plan.n_local, plan.seg_len, n_have)
+    units, keep = _shard_units(eng, plan, n_have, None)
+    if ids is not None:
+        return eng.segment_vectors_host(y32.ctypes.data, units, p, ids)
     return eng.features_host(y32, units, p)
 
 
@@ -149,15 +179,10 @@ def segment_features_sharded(y, sr: int, segment_length_sec: float, features: Se
             rank, world = 0, 1
     lib = engine.lib if engine is not None else None
     plan = plan_segments(int(y.shape[0]), sr, segment_length_sec, overlap_ratio, pad, min_segment_length_sec, rank, world, lib)
+    # aggregation: format_feature_vectors_per_segment (formatters.py:51-163) on the device BEFORE the gather, so the collective
+    # carries [segments, rows] float64 instead of [segments, rows, T] float32
     local = run_shard(y[plan.sample_begin:plan.sample_end], plan, sr, features, frame_length, hop_length, center, window,
-                      feature_params, engine)
+                      feature_params, engine, aggregation=aggregation)
     names = feature_row_names(features, feature_params)
-    if aggregation is not None:
-        # format_feature_vectors_per_segment (formatters.py:51-163) on the device BEFORE the gather: the collective carries
-        # [segments, rows] instead of [segments, rows, T]
-        if not (_is_torch(local) and local.is_cuda):
-            raise ValueError("aggregation= needs the device path (a CUDA tensor as input)")
-        from .core.ml_utils.formatters import aggregate_segments
-        local = aggregate_segments(local, names, aggregation)
     out = gather_features(local, plan, group) if gather else local
     return {"names": names, "features": out, "plan": plan}

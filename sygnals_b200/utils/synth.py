@@ -109,3 +109,35 @@ def torch_mixture_(out, sr: int, seed: int = 1234, unit: int = 0):
     if flat.dim() == 1 and n_units * n < flat.numel():
         flat[n_units * n:] = 0.0
     return out
+
+
+def torch_recording_(out, begin: int, sr: int, seed: int = 1234, chunk_blocks: int = 32):
+    """Fill the 1-D CUDA float32 tensor ``out`` with samples ``[begin, begin + len(out))`` of ONE deterministic, unbounded synthetic
+    recording: one-second blocks of the mixture family (sine + log-chirp + noise, amplitudes over 40 dB).  Position addressable:
+    any slice taken by any rank equals the same slice of the whole recording (blocks are generated in fixed global chunks of
+    ``chunk_blocks`` seconds, each from its own seeds), which is what the strong-scaling bench and the sharded tests need."""
+    import torch
+
+    n = int(out.numel())
+    dev = out.device
+    lo, hi = float(np.log(50.0)), float(np.log(0.45 * sr))
+    t = torch.arange(sr, device=dev, dtype=torch.float32) / sr
+    t64 = t.double()
+    span = chunk_blocks * sr
+    c0, c1 = begin // span, (begin + n + span - 1) // span
+    for c in range(c0, c1):
+        rng = np.random.default_rng([seed, c])
+        f = torch.from_numpy(np.exp(rng.uniform(lo, hi, (chunk_blocks, 3))).astype(np.float32)).to(dev)
+        amp = torch.from_numpy(np.exp(rng.uniform(np.log(0.01), 0.0, (chunk_blocks, 1))).astype(np.float32)).to(dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed * 1000003 + c)
+        ph1 = (2 * np.pi) * torch.remainder(f[:, 0:1] * t[None, :], 1.0)
+        lk = torch.log(f[:, 2:3] / f[:, 1:2]).double()                         # chirp over the one-second block
+        cyc = f[:, 1:2].double() * ((torch.exp(lk * t64[None, :]) - 1.0) / lk)
+        ph2 = (2 * np.pi) * torch.remainder(cyc, 1.0).float()
+        blk = amp * (0.4 * torch.sin(ph1) + 0.4 * torch.sin(ph2) + 0.05 * torch.randn(chunk_blocks, sr, device=dev, generator=g))
+        flat = blk.reshape(-1)
+        g0 = c * span                                                          # global position of the chunk
+        s, e = max(begin, g0), min(begin + n, g0 + span)
+        out[s - begin:e - begin] = flat[s - g0:e - g0]
+    return out

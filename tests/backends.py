@@ -29,6 +29,7 @@ def get_engine(kind: str) -> "_ffi.Engine":
         eng = _ffi.Engine(0, lib)
     else:
         raise ValueError(kind)
+    eng.test_backend = kind                 # tests ask the engine which build it is (never load the emulator to compare)
     _cache[kind] = eng
     return eng
 

@@ -352,8 +352,7 @@ def test_pcm16_ingest_equals_float_path(eng):
 def _dev_buffers(eng, *arrays):
     """'Device' copies of numpy arrays for the engine under test: CUDA tensors on the B200, the arrays themselves on the
     CPU emulator build (whose device memory is host memory).  Returns (holders, pointers)."""
-    from backends import get_engine
-    if eng is get_engine("emu"):
+    if getattr(eng, "test_backend", None) == "emu":
         hold = [np.ascontiguousarray(a) for a in arrays]
         return hold, [h.ctypes.data for h in hold]
     import torch
