@@ -2,7 +2,7 @@
 # `python -m sygnals_b200.build -DNAME=VALUE --out=build/alt/<file>.so`); alternates the two REPS times to average out drift
 ALT=${ALT:?names of the libraries under build/alt}
 cp sygnals_b200/libsygb200.so /tmp/lib_main.so
-line() { python bench.py --hours ${HOURS:-2} --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "
+line() { python bench.py --hours ${HOURS:-2} --steps 5 --warmup 3 --no-e2e --no-cpu --no-weak 2>/dev/null | python -c "
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):

@@ -1,5 +1,5 @@
 # one short device-timed bench line per environment variant: VARS="A=1;B=2" (";"-separated env assignments, "-" = none)
-line() { env $2 python bench.py --hours ${HOURS:-2} --steps 5 --warmup 3 --no-e2e --no-cpu --workload ${WL:-cfg4} 2>/dev/null | python -c "
+line() { env $2 python bench.py --hours ${HOURS:-2} --steps 5 --warmup 3 --no-e2e --no-cpu --no-weak --workload ${WL:-cfg4} 2>/dev/null | python -c "
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):

@@ -58,12 +58,38 @@ def test_native_line_on_the_gpu():
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert (BASE_KEYS - {"cpu_baseline"}) <= set(d) and "impl" not in d
-    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["dtype"] == "f32" and d["scaling"] == "weak"
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["dtype"] == "f32" and d["scaling"] == "strong"
     assert d["gpu_launches"] > 0 and d["value"] > 1e5
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["peak"] > 1000 and 0 < rf["frac"] < 1
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == int(0.1 * 3600 * 44100) * 4 and e["d2h_bytes_per_step"] > 0
-    assert e["matches_device_path"] is True
+    n_seg = d["config"]["segments"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == int(0.1 * 3600 * 44100) * 2 and e["d2h_bytes_per_step"] == n_seg * 24 * 8
+    assert e["matches_device_path"] is True and e["f32"]["h2d_bytes_per_step"] == int(0.1 * 3600 * 44100) * 4
+    assert d["weak"]["value"] > 1e5 and d["roofline"]["aggregate_ms_per_step"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wl,extra", [("cfg3", ["--units", "4000"]), ("cfg2", ["--units", "512", "--nfft", "512,2048"]), ("cfg5", ["--seconds", "20"])])
+def test_secondary_workloads_on_the_gpu(wl, extra):
+    """cfg2 / cfg3 / cfg5 under the same one-line contract (roofline + clocks + e2e)."""
+    r = run_bench("--workload", wl, "--steps", "2", "--warmup", "3", "--no-cpu", "--e2e-steps", "1", *extra)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert (BASE_KEYS - {"cpu_baseline"}) <= set(d) and d["config"]["workload"].startswith(wl)
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and 0 < d["roofline"]["frac"] < 1.2 and d["e2e"]["value"] > 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    if wl == "cfg2":
+        assert [s["n_fft"] for s in d["roofline"]["sweep"]] == [512, 2048]
+
+
+@pytest.mark.parametrize("wl", ["cfg3", "cfg2", "cfg5"])
+def test_reference_arm_secondary_workloads(wl):
+    r = run_bench("--impl", "reference", "--workload", wl, "--steps", "1", "--warmup", "0", "--cpu-units", "8")
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["config"]["workload"].startswith(wl) and d["cpu_baseline"]["kind"] == "port"

@@ -100,9 +100,9 @@ def _scaler_worker(rank, world, port, q):
         X = _scaler_matrix()
         a, b = sdist.shard_range(X.shape[0], rank, world)
         res = {}
-        for kind, params in (("standard", {}), ("minmax", {"feature_range": (-1.0, 2.0)})):
+        for kind, params in (("standard", {}), ("minmax", {"feature_range": (-1.0, 2.0)}), ("robust", {"quantile_range": (10.0, 80.0)})):
             Y, sc = scaling.apply_scaling(torch.from_numpy(X[a:b]), kind, params)
-            res[kind] = (Y.numpy(), sc.scale_, sc.mean_ if kind == "standard" else sc.min_)
+            res[kind] = (Y.numpy(), sc.scale_, {"standard": sc.mean_, "minmax": sc.min_, "robust": sc.center_}[kind])
         q.put((rank, a, b, res))
     finally:
         dist.destroy_process_group()
@@ -118,7 +118,7 @@ def _scaler_matrix():
 
 def test_sharded_scaler_equals_sklearn_two_ranks():
     import torch.multiprocessing as mp
-    from sklearn.preprocessing import MinMaxScaler, StandardScaler
+    from sklearn.preprocessing import MinMaxScaler, RobustScaler, StandardScaler
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -132,11 +132,59 @@ def test_sharded_scaler_equals_sklearn_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     X = _scaler_matrix()
-    ref = {"standard": StandardScaler().fit(X), "minmax": MinMaxScaler(feature_range=(-1.0, 2.0)).fit(X)}
+    ref = {"standard": StandardScaler().fit(X), "minmax": MinMaxScaler(feature_range=(-1.0, 2.0)).fit(X),
+           "robust": RobustScaler(quantile_range=(10.0, 80.0)).fit(X)}
     for kind, sk in ref.items():
         want = sk.transform(X)
         have = np.concatenate([g[3][kind][0] for g in got])
         np.testing.assert_allclose(have, want, rtol=1e-12, atol=1e-12, equal_nan=True)
         for g in got:
             np.testing.assert_allclose(g[3][kind][1], sk.scale_, rtol=1e-12)
-            np.testing.assert_allclose(g[3][kind][2], sk.mean_ if kind == "standard" else sk.min_, rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(g[3][kind][2], {"standard": getattr(sk, "mean_", None), "minmax": getattr(sk, "min_", None),
+                                                       "robust": getattr(sk, "center_", None)}[kind], rtol=1e-12, atol=1e-12)
+
+
+def _agg_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from backends import get_engine
+    from sygnals_b200.utils import synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = get_engine("emu")
+        sr = 8000
+        y = synth.long_signal(int(5.7 * sr), sr, seed=78)
+        r = sdist.segment_features_sharded(y, sr, 1.0, FEATS, overlap_ratio=0.5, frame_length=256, hop_length=128,
+                                           feature_params={"mfcc": {"n_mels": 20, "n_mfcc": 5}}, engine=eng,
+                                           aggregation={"rms_energy": "max", "mfcc_0": "median"})
+        q.put((rank, r["features"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_aggregated_vectors_equal_single_rank():
+    """The bench's strong-scaling path (run_shard with aggregation -> gather of [segments, rows] float64) on two gloo ranks."""
+    import torch.multiprocessing as mp
+    from backends import get_engine
+    from sygnals_b200.utils import synth
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_agg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    eng = get_engine("emu")
+    sr = 8000
+    y = synth.long_signal(int(5.7 * sr), sr, seed=78)
+    one = sdist.segment_features_sharded(y, sr, 1.0, FEATS, overlap_ratio=0.5, frame_length=256, hop_length=128,
+                                         feature_params={"mfcc": {"n_mels": 20, "n_mfcc": 5}}, rank=0, world=1, engine=eng,
+                                         aggregation={"rms_energy": "max", "mfcc_0": "median"})
+    assert one["features"].dtype == np.float64 and one["features"].shape == (12, 8)
+    for _, feats in got:
+        np.testing.assert_array_equal(feats, one["features"])
