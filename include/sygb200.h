@@ -205,6 +205,9 @@ int64_t syg_segment_table(int64_t total_samples, double sr, double segment_lengt
                           int32_t pad, double min_segment_length_sec, int64_t* starts, int32_t* valid, int64_t cap);
 
 /* plan tables, exported for the tests (window [n_fft]; mel basis dense [n_mels][1 + n_fft/2]; dct [n][n_mels]) */
+/* which kernel family the last syg_stft_* call of this process launched: 1 TMA-staged ring kernel, 2 register-staged warp
+ * kernel, 3 CTA-cooperative kernels (tests and bench.py report it) */
+int syg_debug_last_stft_path(void);
 int syg_debug_window(int32_t window, int32_t win_length, int32_t n_fft, float* out);
 int syg_debug_mel_basis(int32_t sr, int32_t n_fft, int32_t n_mels, double fmin, double fmax, float* out);
 int syg_debug_dct(int32_t n_mfcc, int32_t n_mels, int32_t dct_type, int32_t ortho, double lifter, float* out);

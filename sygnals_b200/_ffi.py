@@ -110,6 +110,7 @@ class Library:
             "syg_aggregate_f32": (C.c_int, [vp, vp, i64, i32, i64, vp, vp, i32, vp, vp, vp]),
             "syg_segment_count": (i64, [i64, f64, f64, f64, i32, f64, C.POINTER(i64), C.POINTER(i64)]),
             "syg_segment_table": (i64, [i64, f64, f64, f64, i32, f64, vp, vp, i64]),
+            "syg_debug_last_stft_path": (C.c_int, []),
             "syg_debug_window": (C.c_int, [i32, i32, i32, vp]),
             "syg_debug_mel_basis": (C.c_int, [i32, i32, i32, f64, f64, vp]),
             "syg_debug_dct": (C.c_int, [i32, i32, i32, i32, f64, vp]),

@@ -236,11 +236,19 @@ int warp_fw(int n_fft) {
     switch (ilog2i(n_fft / 2)) { case 4: return 8; case 5: return 8; case 6: return 4; case 7: return 4; case 8: return 2; case 9: return 2; default: return 1; }
 }
 
+int g_last_stft_path = 0;   // 1 ring (TMA-staged), 2 warp kernel (register-staged), 3 CTA-cooperative kernels: what the last STFT call launched
+
 int launch_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
     std::string err;
     static int env = -1;                                                // SYGB200_STFT_BLOCK=1: the CTA-cooperative kernel for every n_fft
     if (env < 0) { const char* e = std::getenv("SYGB200_STFT_BLOCK"); env = e ? std::atoi(e) : 0; }
-    if (n_fft <= 2048 && !env) return launch_rc(syglaunch::frame_warp_stft(n_fft, a, sm_count, st, err), err);
+    if (n_fft <= 2048 && !env) {
+        const int rrc = syglaunch::stft_ring(n_fft, a, sm_count, st, err);      // samples staged by the TMA engine where the layout allows it
+        g_last_stft_path = rrc <= 0 ? 1 : 2;
+        if (rrc <= 0) return launch_rc(rrc, err);
+        return launch_rc(syglaunch::frame_warp_stft(n_fft, a, sm_count, st, err), err);
+    }
+    g_last_stft_path = 3;
     return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_STFT, a, sm_count, st, err), err);
 }
 
@@ -1122,6 +1130,8 @@ int64_t syg_segment_table(int64_t total_samples, double sr, double segment_lengt
     if (n < 0) return fail(SYG_E_BADARG, "%s", err.c_str());
     return n;
 }
+
+int syg_debug_last_stft_path(void) { return g_last_stft_path; }
 
 int syg_debug_window(int32_t window, int32_t win_length, int32_t n_fft, float* out) {
     if (!out) return fail(SYG_E_BADARG, "out is NULL");

@@ -9,6 +9,8 @@ namespace syglaunch {
 // all return 0 or a negative SYG_E_* code (-3 CUDA, -5 unsupported) with a message in err
 int frame_block(int n_fft, int mode, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 int frame_warp(int n_fft, bool extra, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
+// TMA-staged ring kernel; returns 1 when the call is not eligible (the caller then launches frame_warp_stft / frame_block)
+int stft_ring(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 int frame_warp_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err);
 int aggregate(const float* feats, long long n_seg, int n_rows, long long row_stride, const long long* seg_off, const int* seg_len,
