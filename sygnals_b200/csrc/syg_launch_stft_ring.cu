@@ -17,6 +17,7 @@ static int stft_ring_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, s
     if (int rc = prepare_kernel(kfn, RG::NT, smem, kc, &bps, err)) return rc;
     const long long n_rounds = a.g.n_units * (long long)((a.T + RG::TT - 1) / RG::TT);
     if (n_rounds <= 0) return 0;
+    if (n_rounds >= (1LL << 31) || a.g.n_units >= (1LL << 31)) return 1;            // the kernel numbers rounds in 32 bits
     const int grid = (int)std::min<long long>(n_rounds, (long long)sm_count * bps);
     SYG_LAUNCH(kfn, grid, RG::NT, smem, st, a);
     LCK(cudaGetLastError());

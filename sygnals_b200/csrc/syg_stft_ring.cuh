@@ -33,7 +33,12 @@ struct RingGeom {
     static constexpr int NT = NW * 32;
     static constexpr int TT = NW * FW;                                  // frames per round
     static constexpr int TTP = FW * (NW | 1);                           // tile pitch: FW * odd >= TT
-    static constexpr int WF = WT::warp_floats;
+    // Z exchange region of one frame group.  64-bit shared accesses are served one half-warp at a time: the groups of a half-warp
+    // (two for G = 8) must start 2G banks apart, so the pitch is a multiple of 32 words plus 2G mod 32 (WarpTile::RS, tuned for the
+    // 32-bit |X|^2 stores of the feature kernel, is a multiple of 32 plus G: 2x the wavefronts on every exchange access here)
+    static constexpr int ZW = 2 * WT::ZS;                                                        // words a group needs
+    static constexpr int RSR = (FW == 1) ? (ZW + 3) / 4 * 4 : ((ZW - (2 * G) % 32 + 31) / 32 * 32 + (2 * G) % 32);
+    static constexpr int WF = FW * RSR;
     static constexpr int kBarBytes = 64;
     static constexpr int kTableFloats = 2 * M + 2 * M + (M + 4);        // window, twiddles (transposed), half split twiddles
     static constexpr int kTileFloats = ((DB ? 2 : 1) * B * TTP + 3) / 4 * 4;
@@ -48,7 +53,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
     using RG = RingGeom<TL, NW, DB>;
     using WT = typename RG::WT;
     constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, LE = WT::LOG2E;
-    constexpr int Q = E / R2, B = M + 1, NT = RG::NT, TT = RG::TT, TTP = RG::TTP, RSS = WT::RS, WF = RG::WF;
+    constexpr int Q = E / R2, B = M + 1, NT = RG::NT, TT = RG::TT, TTP = RG::TTP, RSS = RG::RSR, WF = RG::WF;
     SYG_DYN_SMEM(smem_raw);
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw);          // [S] "stage full"
     float* const fb = reinterpret_cast<float*>(smem_raw + RG::kBarBytes);
@@ -78,17 +83,27 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
     }
     __syncthreads();
 
-    const int RU = (a.T + TT - 1) / TT;                                                        // rounds per unit
-    const long long n_rounds = a.g.n_units * (long long)RU;
-    const long long stride = gridDim.x;
+    // rounds are numbered in 32 bits (the launcher sends larger problems to the other kernels); units are analytic (start = u * stride)
+    const unsigned RU = (unsigned)((a.T + TT - 1) / TT);                                       // rounds per unit
+    const unsigned n_rounds = (unsigned)a.g.n_units * RU;
+    const unsigned stride = gridDim.x;
+    auto unit_of = [&](unsigned u) {
+        UnitRef r;
+        r.start = (long long)u * a.g.unit_stride;
+        long long v = a.g.total_len - r.start;
+        v = v > a.g.unit_len ? a.g.unit_len : v;
+        r.valid = v < 0 ? 0 : v;
+        return r;
+    };
 
     // producer side (thread 0): arm stage i % S and start the copy of local round i
-    auto issue = [&](long long i) {
-        const long long R = blockIdx.x + i * stride;
-        if (R >= n_rounds) return;
-        const long long u = R / RU;
+    auto issue = [&](unsigned i) {
+        const unsigned long long R64 = blockIdx.x + (unsigned long long)i * stride;
+        if (R64 >= n_rounds) return;
+        const unsigned R = (unsigned)R64;
+        const unsigned u = R / RU;
         const int t0 = (int)(R - u * RU) * TT;
-        const UnitRef ur = unit_ref(a.g, u);
+        const UnitRef ur = unit_of(u);
         const long long base = (long long)t0 * a.hop - a.cpad;
         const int nfr = min(TT, a.T - t0);
         long long lo = base > 0 ? base : 0;
@@ -101,15 +116,16 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
         if (bytes) bulk_g2s(stages + (size_t)s * stage_floats + (lo - base), a.y + ur.start + lo, bytes, &bars[s]);
     };
     if (tid == 0) {
-        for (int i = 0; i < S; ++i) issue(i);
+        for (unsigned i = 0; i < (unsigned)S; ++i) issue(i);
     }
 
-    for (long long i = 0;; ++i) {
-        const long long R = blockIdx.x + i * stride;
-        if (R >= n_rounds) break;                                                              // CTA uniform
-        const long long u = R / RU;
+    for (unsigned i = 0;; ++i) {
+        const unsigned long long R64 = blockIdx.x + (unsigned long long)i * stride;
+        if (R64 >= n_rounds) break;                                                            // CTA uniform
+        const unsigned R = (unsigned)R64;
+        const unsigned u = R / RU;
         const int t0 = (int)(R - u * RU) * TT;
-        const UnitRef ur = unit_ref(a.g, u);
+        const UnitRef ur = unit_of(u);
         const long long base = (long long)t0 * a.hop - a.cpad;
         const int nfr = min(TT, a.T - t0);
         const int s = (int)(i % S);
@@ -207,13 +223,33 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
 
         // ---------------- drain: rows of nfr consecutive frames per bin ----------------
         {
-            constexpr int KS = NT / TT;                                                        // = 32 / FW rows per pass
-            const int sl = tid % TT, kq = tid / TT;
-            if (sl < nfr) {
-                const float* src = tl + kq * TTP + sl;
-                float* dst = reinterpret_cast<float*>(a.stft_out) + ((long long)u * B + kq) * a.T + t0 + sl;
-                const long long dstep = (long long)KS * a.T;
-                for (int k = kq; k < B; k += KS, src += KS * TTP, dst += dstep) *dst = *src;
+            float* const obase = reinterpret_cast<float*>(a.stft_out) + (long long)u * B * a.T + t0;
+            if ((a.T & 1) == 0 && (TT & 1) == 0 && (TTP & 1) == 0 && ((reinterpret_cast<uintptr_t>(obase) & 7u) == 0)) {
+                // even T: every row starts 8-byte aligned -> one 64-bit store per frame pair (half the store instructions)
+                constexpr int HP = TT / 2, KS2 = NT / HP;                                      // pairs per row, rows per pass
+                const int sp = tid % HP, kq = tid / HP;
+                if (2 * sp < nfr) {
+                    const bool both = 2 * sp + 1 < nfr;
+                    const float* src = tl + kq * TTP + 2 * sp;
+                    float* dst = obase + (long long)kq * a.T + 2 * sp;
+                    const long long dstep = (long long)KS2 * a.T;
+                    SYG_UNROLL_BY(4)
+                    for (int k = kq; k < B; k += KS2, src += KS2 * TTP, dst += dstep) {
+                        const float2 v = *reinterpret_cast<const float2*>(src);
+                        if (both) *reinterpret_cast<float2*>(dst) = v;
+                        else *dst = v.x;
+                    }
+                }
+            } else {
+                constexpr int KS = NT / TT;                                                    // = 32 / FW rows per pass
+                const int sl = tid % TT, kq = tid / TT;
+                if (sl < nfr) {
+                    const float* src = tl + kq * TTP + sl;
+                    float* dst = obase + (long long)kq * a.T + sl;
+                    const long long dstep = (long long)KS * a.T;
+                    SYG_UNROLL_BY(4)
+                    for (int k = kq; k < B; k += KS, src += KS * TTP, dst += dstep) *dst = *src;
+                }
             }
         }
     }
