@@ -27,7 +27,7 @@ static int stft_ring_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, s
 // returns 0 (launched), 1 (not eligible: use the register-staged kernels) or a negative error
 int stft_ring(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
     using namespace sygdev;
-    static int mode = -2;                                             // SYGB200_RING: 0 off, 1 default geometry, 2 alternative geometry
+    static int mode = -2;                                             // SYGB200_RING=0: off (A/B against the register-staged kernels)
     if (mode == -2) { const char* e = std::getenv("SYGB200_RING"); mode = e ? std::atoi(e) : 1; }
     if (mode == 0) return 1;
     // eligibility: real output, zero padding, float2-aligned frames, 16-byte aligned bulk copies for every round of every unit
@@ -38,10 +38,10 @@ int stft_ring(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st,
     switch (n_fft) {
         case 256: return stft_ring_t<FftTile<7, 16>, 16, true, 2>(a, sm_count, st, err);
         case 512: return stft_ring_t<FftTile<8, 16>, 16, true, 2>(a, sm_count, st, err);
-        case 1024: return mode == 2 ? stft_ring_t<FftTile<9, 32>, 12, false, 2>(a, sm_count, st, err)
-                                    : stft_ring_t<FftTile<9, 32>, 8, true, 2>(a, sm_count, st, err);
-        case 2048: return mode == 2 ? stft_ring_t<FftTile<10, 32>, 10, false, 2>(a, sm_count, st, err)
-                                    : stft_ring_t<FftTile<10, 32>, 8, true, 2>(a, sm_count, st, err);
+        case 1024: return stft_ring_t<FftTile<9, 32>, 8, true, 2>(a, sm_count, st, err);
+        // measured on B200 (cfg2, round 2): 20 warps for n_fft 512 (no L1 left) 0.485 vs 0.382 ms; single tile + two barriers with
+        // 12 / 10 warps for 1024 / 2048: 0.465 / 0.621 vs 0.471 / 0.489 ms; three stages instead of two: no change
+        case 2048: return stft_ring_t<FftTile<10, 32>, 8, true, 2>(a, sm_count, st, err);
     }
     return 1;
 }
