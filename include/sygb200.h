@@ -205,6 +205,17 @@ int64_t syg_segment_table(int64_t total_samples, double sr, double segment_lengt
                           int32_t pad, double min_segment_length_sec, int64_t* starts, int32_t* valid, int64_t cap);
 
 /* plan tables, exported for the tests (window [n_fft]; mel basis dense [n_mels][1 + n_fft/2]; dct [n][n_mels]) */
+/* Matrix-level forms of the boundary: the reference functions that take a spectrogram (frequency-major, rows x frames).
+ * mfcc(S=log-mel) (sygnals/core/features/cepstral.py:94-117 -> scipy.fftpack.dct(S, axis=-2, type, norm)[:n_mfcc], lifter
+ * M *= 1 + (lifter/2) sin(pi (1..n_mfcc) / lifter)): S [n_units][n_mels][T] float64 -> out [n_units][min(n_mfcc, n_mels)][T] float64.
+ * spectral_contrast(S=|X|) (sygnals/core/features/frequency_domain.py:147-212, librosa defaults: quantile 0.02, dB output, each
+ * of peak / valley clamped 80 dB below its own maximum): S [n_bins][T] float32 magnitudes of an n_fft = 2 (n_bins - 1) transform
+ * -> out [n_bands + 1][T] float32. */
+int syg_mfcc_from_logmel_f64(syg_ctx* ctx, const double* S_dev, int64_t n_units, int32_t n_mels, int64_t T, int32_t n_mfcc,
+                             int32_t dct_type, int32_t dct_ortho, double lifter, double* out_dev, void* stream);
+int syg_spectral_contrast_from_mag_f32(syg_ctx* ctx, const float* S_dev, int32_t n_bins, int64_t T, double sr, int32_t n_bands,
+                                       double fmin, double quantile, float* out_dev, void* stream);
+
 /* which kernel family the last syg_stft_* call of this process launched: 1 TMA-staged ring kernel, 2 register-staged warp
  * kernel, 3 CTA-cooperative kernels (tests and bench.py report it) */
 int syg_debug_last_stft_path(void);

@@ -110,6 +110,8 @@ class Library:
             "syg_aggregate_f32": (C.c_int, [vp, vp, i64, i32, i64, vp, vp, i32, vp, vp, vp]),
             "syg_segment_count": (i64, [i64, f64, f64, f64, i32, f64, C.POINTER(i64), C.POINTER(i64)]),
             "syg_segment_table": (i64, [i64, f64, f64, f64, i32, f64, vp, vp, i64]),
+            "syg_mfcc_from_logmel_f64": (C.c_int, [vp, vp, i64, i32, i64, i32, i32, i32, f64, vp, vp]),
+            "syg_spectral_contrast_from_mag_f32": (C.c_int, [vp, vp, i32, i64, f64, i32, f64, f64, vp, vp]),
             "syg_debug_last_stft_path": (C.c_int, []),
             "syg_debug_window": (C.c_int, [i32, i32, i32, vp]),
             "syg_debug_mel_basis": (C.c_int, [i32, i32, i32, f64, f64, vp]),
@@ -375,6 +377,16 @@ class Engine:
         agg = (C.c_int32 * max(1, len(agg_ids)))(*[int(a) for a in agg_ids])
         self.lib.check(self.lib.dll.syg_segment_vectors_f32(self._h, y_ptr, C.byref(units), C.byref(p), C.addressof(agg), out_ptr,
                                                             stream or None))
+
+    def mfcc_from_logmel_dev(self, S_ptr: int, n_units: int, n_mels: int, T: int, n_mfcc: int, dct_type: int, ortho: bool, lifter: float,
+                             out_ptr: int, stream: int = 0) -> None:
+        self.lib.check(self.lib.dll.syg_mfcc_from_logmel_f64(self._h, S_ptr, int(n_units), int(n_mels), int(T), int(n_mfcc), int(dct_type),
+                                                             int(bool(ortho)), float(lifter), out_ptr, stream or None))
+
+    def spectral_contrast_from_mag_dev(self, S_ptr: int, n_bins: int, T: int, sr: float, n_bands: int, fmin: float, quantile: float,
+                                       out_ptr: int, stream: int = 0) -> None:
+        self.lib.check(self.lib.dll.syg_spectral_contrast_from_mag_f32(self._h, S_ptr, int(n_bins), int(T), float(sr), int(n_bands),
+                                                                       float(fmin), float(quantile), out_ptr, stream or None))
 
     def ingest_pcm_dev(self, raw_ptr: int, fmt: int, channels: int, n_frames: int, out_ptr: int, stream: int = 0) -> None:
         """Interleaved PCM in HBM -> mono float32 in HBM (load_audio(mono=True) arithmetic)."""

@@ -22,6 +22,15 @@
 #include "syg_launch.h"
 #include "syg_plan.h"
 
+// NVTX ranges around every compute entry point (tracing): visible in nsys / ncu timelines, free when no tool is attached
+#ifndef SYG_EMU
+#include <nvtx3/nvToolsExt.h>
+namespace { struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } }; }
+#else
+namespace { struct NvtxRange { explicit NvtxRange(const char*) {} }; }
+#endif
+#define SYG_TRACE() NvtxRange nvtx_range_(__func__)
+
 namespace {
 
 thread_local std::string g_err;
@@ -838,6 +847,7 @@ int64_t syg_frame_count(int64_t n_samples, int32_t frame_length, int32_t hop_len
 
 int syg_features_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, const syg_feature_params* p,
                      float* out_dev, void* stream) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     int rc = check_units(units);
     if (rc) return rc;
@@ -870,6 +880,7 @@ int syg_features_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, c
 // agg == nullptr: out_host is float32 [n_units][n_rows][T];  else: float64 [n_units][n_rows] (per-row SYG_AGG_* over the frames)
 static int features_host_impl(syg_ctx* ctx, const void* y_host, InFmt inf, const syg_units* units, const syg_feature_params* p,
                               const int32_t* agg, void* out_host) {
+    NvtxRange nvtx_range_(agg ? "syg_segment_vectors_host" : "syg_features_host");
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     if (inf.fmt >= 0 && (inf.fmt > SYG_PCM_F32 || inf.channels < 1 || inf.channels > 64))
         return fail(SYG_E_BADARG, "bad PCM layout (format %d, %d channels)", inf.fmt, inf.channels);
@@ -941,6 +952,7 @@ int syg_segment_vectors_host_pcm(syg_ctx* ctx, const void* raw_host, int32_t sam
 
 int syg_segment_vectors_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, const syg_feature_params* p,
                             const int32_t* agg, double* out_dev, void* stream) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     if (!agg) return fail(SYG_E_BADARG, "agg is NULL");
     int rc = check_units(units);
@@ -982,6 +994,7 @@ int syg_segment_vectors_f32(syg_ctx* ctx, const float* y_dev, const syg_units* u
 
 int syg_ingest_pcm(syg_ctx* ctx, const void* raw_dev, int32_t sample_format, int32_t channels, int64_t n_frames, float* mono_dev,
                    void* stream) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     if (n_frames < 0 || (n_frames > 0 && (!raw_dev || !mono_dev))) return fail(SYG_E_BADARG, "bad PCM buffer");
     if (sample_format < SYG_PCM_U8 || sample_format > SYG_PCM_F32) return fail(SYG_E_BADARG, "unknown PCM sample format %d", sample_format);
@@ -993,6 +1006,7 @@ int syg_ingest_pcm(syg_ctx* ctx, const void* raw_dev, int32_t sample_format, int
 }
 
 int syg_pcm16_to_f32(syg_ctx* ctx, const int16_t* in_dev, float* out_dev, int64_t n, void* stream) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     if (n < 0 || (n > 0 && (!in_dev || !out_dev))) return fail(SYG_E_BADARG, "bad pcm16 buffer");
     ENTER_DEVICE(ctx);
@@ -1007,6 +1021,7 @@ static size_t stft_elem_bytes(int out_kind) { return out_kind == SYG_OUT_COMPLEX
 int syg_stft_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, int32_t n_fft, int32_t hop_length,
                  int32_t win_length, int32_t window, int32_t center, int32_t pad_mode, int32_t out_kind,
                  void* out_dev, void* stream) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     int rc = check_units(units);
     if (rc) return rc;
@@ -1028,6 +1043,7 @@ int syg_stft_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, int32
 int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, int32_t n_fft, int32_t hop_length,
                       int32_t win_length, int32_t window, int32_t center, int32_t pad_mode, int32_t out_kind,
                       void* out_host) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     int rc = check_host_units(units);
     if (rc) return rc;
@@ -1054,6 +1070,7 @@ int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units,
 int syg_psd_welch_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, double fs, int32_t window,
                       int32_t nperseg, int32_t noverlap, int32_t nfft, int32_t detrend_constant, int32_t scaling,
                       float* psd_dev, float* stats_dev, void* stream) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     int rc = check_units(units);
     if (rc) return rc;
@@ -1074,6 +1091,7 @@ int syg_psd_welch_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, 
 int syg_psd_welch_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units, double fs, int32_t window,
                            int32_t nperseg, int32_t noverlap, int32_t nfft, int32_t detrend_constant,
                            int32_t scaling, float* psd_host, float* stats_host) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     int rc = check_host_units(units);
     if (rc) return rc;
@@ -1100,6 +1118,7 @@ int syg_psd_welch_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* u
 int syg_aggregate_f32(syg_ctx* ctx, const float* feats_dev, int64_t n_seg, int32_t n_rows, int64_t row_stride,
                       const int64_t* seg_off_dev, const int32_t* seg_len_dev, int32_t fixed_len, const int32_t* agg,
                       double* out_dev, void* stream) {
+    SYG_TRACE();
     if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
     if (n_seg < 0 || n_rows < 0 || row_stride < 0) return fail(SYG_E_BADARG, "negative aggregation geometry");
     if (n_seg == 0 || n_rows == 0) return SYG_OK;
@@ -1129,6 +1148,70 @@ int64_t syg_segment_table(int64_t total_samples, double sr, double segment_lengt
                                        min_segment_length_sec, nullptr, nullptr, starts, valid, cap, err);
     if (n < 0) return fail(SYG_E_BADARG, "%s", err.c_str());
     return n;
+}
+
+int syg_mfcc_from_logmel_f64(syg_ctx* ctx, const double* S_dev, int64_t n_units, int32_t n_mels, int64_t T, int32_t n_mfcc,
+                             int32_t dct_type, int32_t dct_ortho, double lifter, double* out_dev, void* stream) {
+    SYG_TRACE();
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    if (n_units < 0 || T < 0 || n_mels < 1 || n_mels > 4096) return fail(SYG_E_BADARG, "bad log-mel matrix geometry");
+    if (n_mfcc < 1) return fail(SYG_E_BADARG, "n_mfcc must be positive");
+    if (n_units == 0 || T == 0) return SYG_OK;
+    if (!S_dev || !out_dev) return fail(SYG_E_BADARG, "NULL device pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ENTER_DEVICE(ctx);
+    // scipy's dct(...)[:n_mfcc] keeps min(n_mfcc, n_mels) rows; the table holds exactly those
+    const int C = std::min(n_mfcc, n_mels);
+    std::string dk = keyf("dct64:%d:%d:%d:%d:%.9g:m%d", C, n_mels, dct_type, dct_ortho, lifter, n_mfcc);
+    std::vector<double> dct;
+    if (!ctx->tables.count(dk)) {
+        std::string err;
+        if (!sygplan::build_dct(C, n_mels, dct_type, dct_ortho != 0, lifter, n_mfcc, dct, err)) return fail(SYG_E_BADARG, "%s", err.c_str());
+    }
+    const double* d_dct = nullptr;
+    int rc = upload_table(ctx, dk, dct, &d_dct);
+    if (rc) return rc;
+    std::string err;
+    rc = syglaunch::dct_matrix(S_dev, d_dct, n_units, n_mels, T, C, out_dev, ctx->sm_count, reinterpret_cast<cudaStream_t>(stream), err);
+    return rc ? fail(rc, "%s", err.c_str()) : SYG_OK;
+}
+
+int syg_spectral_contrast_from_mag_f32(syg_ctx* ctx, const float* S_dev, int32_t n_bins, int64_t T, double sr, int32_t n_bands,
+                                       double fmin, double quantile, float* out_dev, void* stream) {
+    SYG_TRACE();
+    if (!ctx) return fail(SYG_E_BADARG, "ctx is NULL");
+    if (n_bins < 2 || T < 0) return fail(SYG_E_BADARG, "bad spectrogram geometry");
+    if (T == 0) return SYG_OK;
+    if (!S_dev || !out_dev) return fail(SYG_E_BADARG, "NULL device pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ENTER_DEVICE(ctx);
+    sygplan::Bands b;
+    std::string err;
+    if (!sygplan::build_bands(sr, 2 * (n_bins - 1), n_bands, fmin, quantile, b, err)) return fail(SYG_E_BADARG, "%s", err.c_str());
+    int nq[syg::kMaxBands];
+    for (int i = 0; i < b.nb; ++i) nq[i] = std::max(1, std::min(b.nq[i], std::max(b.cnt[i], 1)));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // workspace: unit maxima (one "unit" = the whole matrix: power_to_db clamps 80 dB below the array maximum) + linear peaks / valleys
+    const size_t need = 256 + (size_t)T * 2 * b.nb * sizeof(float);
+    if (ctx->ws_done) CK(cudaStreamWaitEvent(st, ctx->ws_done, 0));
+    else CK(cudaEventCreateWithFlags(&ctx->ws_done, cudaEventDisableTiming));
+    if (need > ctx->ws.cap) CK(cudaStreamSynchronize(st));
+    int rc = ctx->ws.ensure(need);
+    if (rc) return rc;
+    struct Done { syg_ctx* c; cudaStream_t s; ~Done() { cudaEventRecord(c->ws_done, s); } } done_{ctx, st};
+    unsigned* um = reinterpret_cast<unsigned*>(ctx->ws.p);
+    float* cws = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->ws.p) + 256);
+    CK(cudaMemsetAsync(um, 0, 4 * sizeof(unsigned), st));
+    rc = syglaunch::contrast_spectrum(S_dev, n_bins, T, b.nb, b.lo, b.cnt, nq, cws, um, ctx->sm_count, st, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    syg::FinalizeArgs f;
+    std::memset(&f, 0, sizeof(f));
+    f.n_units = 1; f.T = (int)T; f.n_rows = b.nb; f.row_mfcc = -1; f.nb = b.nb; f.row_contrast = 0; f.amin = 1e-10f; f.top_db = 80.0f;
+    f.cws = cws; f.unit_max = um; f.out = out_dev;
+    if (T > 0x7fffffffLL) return fail(SYG_E_UNSUPPORTED, "too many frames");
+    const long long n_tiles = (T + sygdev::kFinTT - 1) / sygdev::kFinTT;
+    rc = syglaunch::finalize(f, (unsigned)std::min<long long>(n_tiles, 0x7fffffffLL), 1u, 256, st, err);
+    return rc ? fail(rc, "%s", err.c_str()) : SYG_OK;
 }
 
 int syg_debug_last_stft_path(void) { return g_last_stft_path; }

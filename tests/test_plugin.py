@@ -120,3 +120,70 @@ def test_routed_extract_features_matches_oracle_on_gpu():
             np.testing.assert_allclose(got[k], ref[k], rtol=1e-5, atol=1e-7)
     df = fn(y, sr, feats)                                                         # DataFrame contract (manager.py:430-442)
     assert df.index.name == "time" and list(df.columns) == [k for k in ref if k != "time"]
+
+
+def test_mixed_request_is_split_and_paths_are_logged(caplog):
+    """Kernelled features stay on the engine, the others go to the reference, columns come back in the requested order; every
+    hand-over to the reference is a WARNING naming the path (once per reason).  Engine and reference are stand-ins here."""
+    p = plg.SygnalsB200Plugin()
+    calls = {}
+
+    def fake_ref(y, sr, features, **kw):
+        calls["ref"] = list(features)
+        out = {"time": np.arange(3.0)}
+        out.update({f: np.full(3, 7.0) for f in features})
+        return out
+
+    import sygnals_b200.core.features.manager as m
+    real = m.extract_features
+
+    def fake_engine(y, sr, features, **kw):
+        calls["eng"] = list(features)
+        assert kw["output_format"] == "dict_of_arrays"
+        out = {"time": np.arange(3.0)}
+        for f in features:
+            for col in ([f"mfcc_{i}" for i in range(2)] if f == "mfcc" else [f]):
+                out[col] = np.full(3, 1.0)
+        return out
+
+    m.extract_features = fake_engine
+    try:
+        fn = p.make_extract_features(original=fake_ref)
+        with caplog.at_level(logging.WARNING, logger="sygnals_b200.plugin"):
+            got = fn(np.zeros(4096), 22050, ["jitter", "mfcc", "rms_energy", "hnr"], feature_params={"mfcc": {"n_mfcc": 2}},
+                     output_format="dict_of_arrays")
+            fn(np.zeros(4096), 22050, ["jitter", "mfcc"], feature_params={"mfcc": {"n_mfcc": 2}}, output_format="dict_of_arrays")
+        assert calls["eng"] == ["mfcc"] and list(got) == ["time", "jitter", "mfcc_0", "mfcc_1", "rms_energy", "hnr"]
+        assert got["jitter"][0] == 7.0 and got["mfcc_1"][0] == 1.0
+        warned = [r.message for r in caplog.records if "REFERENCE (CPU) implementation" in r.message]
+        assert len(warned) == 2 and "no CUDA kernel for ['jitter', 'hnr']" in warned[0]      # two distinct reasons, each once
+        df = fn(np.zeros(4096), 22050, ["jitter", "mfcc"], feature_params={"mfcc": {"n_mfcc": 2}})
+        assert df.index.name == "time" and list(df.columns) == ["jitter", "mfcc_0", "mfcc_1"]
+        # a NotImplementedError raised by the engine after the routing checks also lands on the reference (non-strict)
+        def refusing(y, sr, features, **kw):
+            raise NotImplementedError("n_mels=300: supported range is [1, 256]")
+        m.extract_features = refusing
+        calls.clear()
+        fn(np.zeros(4096), 22050, ["mfcc"], output_format="dict_of_arrays")
+        assert calls["ref"] == ["mfcc"]
+        p._strict = True
+        with pytest.raises(NotImplementedError):
+            p.make_extract_features(original=fake_ref)(np.zeros(4096), 22050, ["mfcc"], output_format="dict_of_arrays")
+    finally:
+        m.extract_features = real
+
+
+def test_psd_wrappers_accept_positional_arguments():
+    """compute_psd_welch(x, fs, window, nperseg, noverlap, nfft, ...) positionally, as the reference signature allows (dsp.py:495)."""
+    p = plg.SygnalsB200Plugin()
+    seen = {}
+
+    def ref(x, fs=1.0, window="hann", **kw):
+        seen.update(kw)
+        return "ref"
+
+    fn = p._make_psd("compute_psd_welch", ref)
+    assert fn(np.zeros(3000), 1000.0, "hann", 1000, 500) == "ref"        # nperseg 1000 is not a power of two -> reference, same arguments
+    assert seen == {"nperseg": 1000, "noverlap": 500}
+    with pytest.raises(TypeError):
+        fn(np.zeros(3000), 1000.0, "hann", 1000, nperseg=512)
