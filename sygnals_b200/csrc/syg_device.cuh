@@ -569,7 +569,10 @@ SYG_DEVICE SYG_INLINE uint4 refill4(const float* __restrict__ q, int mine, unsig
 // constants at the call site (band-specialised kernel): every loop below unrolls completely.
 template <bool ST>
 SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p, int lo, int count, int n) {
-    constexpr int UP = ST ? 32 : 1;
+#ifndef SYG_POP_UNROLL
+#define SYG_POP_UNROLL 3     // measured on B200 (cfg4): 3 / 5 / 8 / 32 -> 6.540 / 6.571 / 6.586 / 6.584 ms per 2 h (instruction-cache footprint)
+#endif
+    constexpr int UP = ST ? SYG_POP_UNROLL : 1;
     const int lane = threadIdx.x & 31;
     const float* q = p + ppad(lo + lane);
     const int mine = max((count - lane + 31) >> 5, 0);         // elements this lane owns
