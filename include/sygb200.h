@@ -217,7 +217,7 @@ int syg_spectral_contrast_from_mag_f32(syg_ctx* ctx, const float* S_dev, int32_t
                                        double fmin, double quantile, float* out_dev, void* stream);
 
 /* which kernel family the last syg_stft_* call of this process launched: 1 TMA-staged ring kernel, 2 register-staged warp
- * kernel, 3 CTA-cooperative kernels (tests and bench.py report it) */
+ * kernel, 3 CTA-cooperative kernels, 4 sub-FFT kernel for n_fft 4096 / 8192 (tests and bench.py report it) */
 int syg_debug_last_stft_path(void);
 int syg_debug_window(int32_t window, int32_t win_length, int32_t n_fft, float* out);
 int syg_debug_mel_basis(int32_t sr, int32_t n_fft, int32_t n_mels, double fmin, double fmax, float* out);

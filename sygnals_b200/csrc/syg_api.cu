@@ -208,6 +208,20 @@ int get_fft_tables(syg_ctx* ctx, int n_fft, const float2** tw, const float2** tw
     return upload_table(ctx, k2, b, tws);
 }
 
+// [n_fft/4 + 1] entries 0.5 exp(-2 pi i k / n_fft): the real split with the halving folded into the twiddle
+int get_half_split_twiddles(syg_ctx* ctx, int n_fft, const float2** out) {
+    std::string kh = keyf("twsh:%d", n_fft);
+    std::vector<float2> h;
+    if (!ctx->tables.count(kh)) {
+        h.resize(n_fft / 4 + 1);
+        for (int k = 0; k <= n_fft / 4; ++k) {
+            const double ang = -2.0 * sygplan::kPi * (double)k / (double)n_fft;
+            h[k] = make_float2((float)(0.5 * std::cos(ang)), (float)(0.5 * std::sin(ang)));
+        }
+    }
+    return upload_table(ctx, kh, h, out);
+}
+
 int get_window(syg_ctx* ctx, int window, int win_length, int n_fft, bool centred, const float** out) {
     std::string key = keyf("win:%d:%d:%d:%d", window, win_length, n_fft, (int)centred);
     std::vector<float> w;
@@ -245,12 +259,16 @@ int warp_fw(int n_fft) {
     switch (ilog2i(n_fft / 2)) { case 4: return 8; case 5: return 8; case 6: return 4; case 7: return 4; case 8: return 2; case 9: return 2; default: return 1; }
 }
 
-int g_last_stft_path = 0;   // 1 ring (TMA-staged), 2 warp kernel (register-staged), 3 CTA-cooperative kernels: what the last STFT call launched
+int g_last_stft_path = 0;   // 1 ring (TMA-staged), 2 warp kernel (register-staged), 3 CTA-cooperative kernels, 4 sub-FFT kernel (n_fft 4096 / 8192): last STFT launch
 
 int launch_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
     std::string err;
     static int env = -1;                                                // SYGB200_STFT_BLOCK=1: the CTA-cooperative kernel for every n_fft
     if (env < 0) { const char* e = std::getenv("SYGB200_STFT_BLOCK"); env = e ? std::atoi(e) : 0; }
+    if (n_fft >= 4096 && !env && a.out_kind != 0) {
+        g_last_stft_path = 4;
+        return launch_rc(syglaunch::stft_big(n_fft, a, sm_count, st, err), err);
+    }
     if (n_fft <= 2048 && !env) {
         const int rrc = syglaunch::stft_ring(n_fft, a, sm_count, st, err);      // samples staged by the TMA engine where the layout allows it
         g_last_stft_path = rrc <= 0 ? 1 : 2;
@@ -376,18 +394,7 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
     if (rc) return rc;
     rc = get_fft_tables(ctx, fl, &a.tw, &a.tws);
     if (rc) return rc;
-    {
-        std::string kh = keyf("twsh:%d", fl);
-        std::vector<float2> h;
-        if (!ctx->tables.count(kh)) {
-            h.resize(fl / 4 + 1);
-            for (int k = 0; k <= fl / 4; ++k) {
-                const double ang = -2.0 * sygplan::kPi * (double)k / (double)fl;
-                h[k] = make_float2((float)(0.5 * std::cos(ang)), (float)(0.5 * std::sin(ang)));
-            }
-        }
-        if ((rc = upload_table(ctx, kh, h, &a.twsh))) return rc;
-    }
+    if ((rc = get_half_split_twiddles(ctx, fl, &a.twsh))) return rc;
     size_t ws = 0;
     if (mask & syg::FB_MFCC) {
         if (p->n_mels < 1 || p->n_mels > 256) return fail(SYG_E_UNSUPPORTED, "n_mels=%d: supported range is [1, 256]", p->n_mels);
@@ -686,6 +693,11 @@ int stft_setup(syg_ctx* ctx, const syg_units* u, int n_fft, int hop, int win_len
     a.out_kind = out_kind;
     int rc = get_window(ctx, window, win_length, n_fft, true, &a.window);
     if (rc) return rc;
+    if (n_fft >= 4096) {                                                // stft_big_kernel: 1024-point sub-transforms + recombination
+        const float2* unused = nullptr;
+        if ((rc = get_fft_tables(ctx, 2048, &a.tw1k, &unused))) return rc;
+        if ((rc = get_half_split_twiddles(ctx, n_fft, &a.twsh))) return rc;
+    }
     return get_fft_tables(ctx, n_fft, &a.tw, &a.tws);
 }
 

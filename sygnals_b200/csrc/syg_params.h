@@ -53,7 +53,8 @@ struct FrameArgs {
     const float* window;        // [n_fft], already zero-padded/centred to n_fft
     const float2* tw;           // [M]      exp(-2 pi i k / M)
     const float2* tws;          // [M/2+1]  exp(-2 pi i k / n_fft)
-    const float2* twsh;         // [M/2+1]  0.5 exp(-2 pi i k / n_fft)   (warp feature kernel: split with the halving folded in)
+    const float2* twsh;         // [M/2+1]  0.5 exp(-2 pi i k / n_fft)   (split with the halving folded in)
+    const float2* tw1k;         // [1024]   exp(-2 pi i k / 1024): sub-transform twiddles of stft_big_kernel (n_fft 4096 / 8192)
     // ---- features
     unsigned mask;
     double bin_hz;              // frequency of bin 1 (numpy rfftfreq step)

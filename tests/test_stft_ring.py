@@ -105,3 +105,28 @@ def test_ring_equals_register_staged_kernel(eng):
         eng.stft_dev(yo.ctypes.data + 4, eng.units_clips(3, L), n_fft, hop, n_fft, 0, True, 0, _ffi.OUT_MAGNITUDE, out.ctypes.data)
         assert eng.lib.dll.syg_debug_last_stft_path() == 2
         np.testing.assert_allclose(out, a, rtol=2e-5, atol=1e-6 * a.max())
+
+
+@pytest.mark.parametrize("n_fft,hop,L,n,kind,pad", [
+    (4096, 1024, 16000, 2, _ffi.OUT_MAGNITUDE, 0),     # cfg2 shapes: T = 16 (two rounds of 8 frames per clip)
+    (8192, 2048, 16000, 3, _ffi.OUT_MAGNITUDE, 0),     # T = 8; rounds of 4 frames straddle clips when n is odd
+    (4096, 700, 9001, 3, _ffi.OUT_POWER, 0),           # ragged length, hop not a divisor, odd positions (unaligned pairs)
+    (8192, 1000, 30000, 1, _ffi.OUT_POWER, 1),         # reflect padding goes through the predicated loads
+    (4096, 1024, 3000, 2, _ffi.OUT_MAGNITUDE, 0),      # unit shorter than the frame
+])
+def test_big_transforms_vs_oracle(eng, n_fft, hop, L, n, kind, pad):
+    """n_fft 4096 / 8192 through stft_big_kernel (1024-point sub-FFTs + recombination) against the oracle's compute_stft."""
+    y = np.stack([synth.mixture(L, 16000, seed=17 * n_fft + i) for i in range(n)]).astype(np.float32)
+    if n > 2:
+        y[1] = synth.edge_clip("impulse", L, 16000)
+    out = eng.stft_host(y.reshape(-1), eng.units_clips(n, L), n_fft, hop, n_fft, 0, True, pad, kind)
+    assert eng.lib.dll.syg_debug_last_stft_path() == 4, "the sub-FFT kernel did not run"
+    for i in range(n):
+        S = np.abs(orc.compute_stft(y[i].astype(np.float64), n_fft=n_fft, hop_length=hop, win_length=n_fft, window="hann", center=True,
+                                    pad_mode="reflect" if pad else "constant"))
+        _check(out[i].astype(np.float64), S * S if kind == _ffi.OUT_POWER else S, kind == _ffi.OUT_POWER)
+    # complex output of the same transform still comes from the CTA-cooperative kernel and agrees
+    c = eng.stft_host(y.reshape(-1), eng.units_clips(n, L), n_fft, hop, n_fft, 0, True, pad, _ffi.OUT_COMPLEX)
+    assert eng.lib.dll.syg_debug_last_stft_path() == 3
+    ref = np.abs(c) ** 2 if kind == _ffi.OUT_POWER else np.abs(c)
+    np.testing.assert_allclose(out, ref, rtol=3e-4 if kind == _ffi.OUT_POWER else 1.5e-4, atol=2e-6 * ref.max())
