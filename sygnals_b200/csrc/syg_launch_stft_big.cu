@@ -20,8 +20,8 @@ static int stft_big_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, st
 }
 
 int stft_big(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err) {
-    if (n_fft == 4096) return stft_big_t<2, 16>(a, sm_count, st, err);      // 8 frames per round: 8 x 2 x 8.3 KB regions + 72 KB tile
-    if (n_fft == 8192) return stft_big_t<4, 8>(a, sm_count, st, err);       // 4 frames per round: 4 x 4 x 8.3 KB regions + 80 KB tile
+    if (n_fft == 4096) return stft_big_t<2, 16>(a, sm_count, st, err);      // 16 warps, 8 frames per round: 8 x 2 x 8.3 KB regions + 72 KB tile
+    if (n_fft == 8192) return stft_big_t<4, 16>(a, sm_count, st, err);      // 16 warps, 4 frames per round: 4 x 4 x 8.3 KB regions + 80 KB tile
     err = "stft_big: n_fft must be 4096 or 8192";
     return -5;
 }

@@ -4,7 +4,7 @@
 // (n_fft 4096 / 8192), built from the warp-synchronous 1024-point register FFT of the smaller transforms.
 //
 // The packed frame z[n] = x[2n] + i x[2n+1], n < M = 1024 R, is decimated into R interleaved sub-sequences z_r[m] = z[R m + r].  Two
-// warps own a frame: each runs R/2 of the sub-FFTs (radix-32 x radix-32 in registers, FP32x2 butterflies, one exchange through a
+// warps own a frame (R of them: one sub-FFT each) (radix-32 x radix-32 in registers, FP32x2 butterflies, one exchange through a
 // private shared-memory region, natural-order result Z_r left there), then -- after a CTA barrier -- the 64 lanes of the pair share
 // the recombination: for a residue q < 1024
 //     Z[q + 1024 a] = sum_r W_R^{r a} (W_M^{r q} Z_r[q])        (an R-point butterfly over the twiddled sub-spectra)
@@ -28,15 +28,30 @@ struct BigGeom {
     static constexpr int MS = 1024;                                    // points of a sub-FFT
     static constexpr int M = MS * R, B = M + 1;
     static constexpr int NT = NW * 32;
-    static constexpr int TT = NW / 2;                                  // frames per round (two warps per frame)
+    static constexpr int WPF = R;                                      // warps per frame: one sub-FFT each
+    static constexpr int TT = NW / WPF;                                // frames per round
     static constexpr int TTP = TT | 1;                                 // odd tile pitch: bins along the lanes never collide
-    static constexpr int RW = R / 2;                                   // sub-FFTs per warp
-    static constexpr int ZF = (2 * WT::ZS + 3) / 4 * 4;                // floats of one sub-spectrum region (zpad layout)
+    // floats of one sub-spectrum region (zpad layout).  R = 4: regions 8 banks apart (ZF = 8 mod 32), so that the staging stores of a
+    // half-warp -- points of sub-sequences r and r + 2 at the same index -- fall on disjoint banks
+    static constexpr int ZF = (R == 4) ? 2120 : (2 * WT::ZS + 3) / 4 * 4;
+    static_assert(ZF >= 2 * WT::ZS, "region holds the padded sub-spectrum");
     static constexpr int kTwFloats = 2 * MS;                           // transposed pass-2 twiddles of the sub-FFT
     static constexpr int kTileFloats = (B * TTP + 3) / 4 * 4;
     static constexpr size_t bytes = sizeof(float) * ((size_t)kTwFloats + (size_t)TT * R * ZF + kTileFloats);
     static_assert(R == 2 || R == 4, "n_fft 4096 or 8192");
 };
+
+// the warps that share a frame (named barrier 1 + slot); the CPU emulator has CTA barriers only, and every warp
+// of the CTA reaches this point once per round, so a CTA barrier is an equivalent superset there
+template <int THREADS>
+SYG_DEVICE SYG_INLINE void frame_barrier(int slot) {
+#ifdef SYG_EMU
+    (void)slot;
+    __syncthreads();
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(THREADS) : "memory");
+#endif
+}
 
 // (a + i b) * (c + i d)
 SYG_DEVICE SYG_INLINE float2 cmulf(float2 x, float2 w) {
@@ -66,7 +81,8 @@ template <int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) stft_big_kernel(const syg::FrameArgs a) {
     using BG = BigGeom<R, NW>;
     using WT = typename BG::WT;
-    constexpr int E = 32, G = 32, MS = BG::MS, M = BG::M, B = BG::B, NT = BG::NT, TT = BG::TT, TTP = BG::TTP, RW = BG::RW, ZF = BG::ZF, LE = 5;
+    constexpr int E = 32, G = 32, MS = BG::MS, M = BG::M, B = BG::B, NT = BG::NT, TT = BG::TT, TTP = BG::TTP, WPF = BG::WPF, ZF = BG::ZF, LE = 5;
+    constexpr int LPF = 32 * WPF;                                                              // lanes per frame
     SYG_DYN_SMEM(smem_raw);
     float* const fb = reinterpret_cast<float*>(smem_raw);
     float2* const t_tw = reinterpret_cast<float2*>(fb);                                        // [32][32] W_1024^{r k} (transposed)
@@ -74,7 +90,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_big_kernel(const syg::FrameAr
     float* const tile = regions + (size_t)TT * R * ZF;                                         // [B][TTP]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int slot = warp >> 1, half = warp & 1;                                               // frame of the round, which warp of its pair
+    const int slot = warp / WPF, sub = warp % WPF;                                             // frame of the round, this warp's sub-sequence
     float* const freg = regions + (size_t)slot * R * ZF;                                       // this frame's R sub-spectra
 
     for (int i = tid; i < MS; i += NT) t_tw[i] = __ldg(a.tw1k + (i / E) * (i % E));
@@ -90,31 +106,49 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_big_kernel(const syg::FrameAr
         if (!valid) ur.valid = 0;
         const long long p0 = (long long)t * a.hop - a.cpad;
 
-        // ---------------- this warp's sub-FFTs: z_r[m] = z[R m + r], r = half * RW + s ----------------
-        SYG_UNROLL
-        for (int s = 0; s < RW; ++s) {
-            const int r = half * RW + s;
-            float2* const zs = reinterpret_cast<float2*>(freg + (size_t)r * ZF);
-            float2 z[E];
-            {
-                const float* src = a.y + ur.start + p0;
-                const bool interior = valid && p0 >= 0 && p0 + 2 * M <= ur.valid && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
-                const float2* w2 = reinterpret_cast<const float2*>(a.window);
-                if (__all_sync(kFull, interior)) {
-                    SYG_UNROLL
-                    for (int i = 0; i < E; ++i) {
-                        const int c = R * (lane + i * G) + r;                                  // packed point index in the frame
-                        z[i] = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(src) + c), __ldg(w2 + c));
-                    }
-                } else {
-                    SYG_UNROLL
-                    for (int i = 0; i < E; ++i) {
-                        const int c = R * (lane + i * G) + r;
-                        const float2 v = load_pair(a.y, ur, p0 + 2 * c, a.pad_mode);
-                        z[i] = __fmul2_rn(v, __ldg(w2 + c));
-                    }
+        // ---------------- stage the windowed frame, de-interleaved, in the R regions ----------------
+        // The two warps of the pair read the frame with coalesced 16-byte loads (a strided read of one sub-sequence would use a
+        // quarter / half of every sector it touches) and scatter packed point n = R m + r to region r, index m (linear layout;
+        // the sub-FFT's first pass then reads index lane + 32 i without conflicts and overwrites the region in the padded layout).
+        {
+            const int L = sub * 32 + lane;                                                     // lane within the frame's group of warps
+            constexpr int C4 = M / (2 * LPF);                                                  // float4 chunks (two packed points) per lane
+            const float* src = a.y + ur.start + p0;
+            const bool interior = valid && p0 >= 0 && p0 + 2 * M <= ur.valid && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+            const float4* w4 = reinterpret_cast<const float4*>(a.window);
+            auto put = [&](int n, float2 v) {                                                  // packed point n of the frame
+                reinterpret_cast<float2*>(freg + (size_t)(n % R) * ZF)[n / R] = v;
+            };
+            if (__all_sync(kFull, interior)) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                SYG_UNROLL_BY(8)
+                for (int i = 0; i < C4; ++i) {
+                    const int c4 = L + LPF * i;
+                    const float4 v = __ldg(s4 + c4), w = __ldg(w4 + c4);
+                    put(2 * c4, make_float2(v.x * w.x, v.y * w.y));
+                    put(2 * c4 + 1, make_float2(v.z * w.z, v.w * w.w));
+                }
+            } else {
+                SYG_UNROLL_BY(4)
+                for (int i = 0; i < C4; ++i) {
+                    const int c4 = L + LPF * i;
+                    const float4 w = __ldg(w4 + c4);
+                    const float2 v0 = load_pair(a.y, ur, p0 + 4 * c4, a.pad_mode), v1 = load_pair(a.y, ur, p0 + 4 * c4 + 2, a.pad_mode);
+                    put(2 * c4, make_float2(v0.x * w.x, v0.y * w.y));
+                    put(2 * c4 + 1, make_float2(v1.x * w.z, v1.y * w.w));
                 }
             }
+        }
+        frame_barrier<LPF>(slot);
+
+        // ---------------- this warp's sub-FFT: z_r[m] = z[R m + r], r = sub ----------------
+        {
+            const int r = sub;
+            float2* const zs = reinterpret_cast<float2*>(freg + (size_t)r * ZF);
+            float2 z[E];
+            SYG_UNROLL
+            for (int i = 0; i < E; ++i) z[i] = zs[lane + i * G];
+            __syncwarp();                                                                      // all inputs are in registers before the scatter
             dft_dif_p<E, 1>(z);
             SYG_UNROLL
             for (int kp = 0; kp < E; ++kp) zs[zpad<LE>(lane * E + kp)] = z[bitrev(kp, LE)];
@@ -135,7 +169,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_big_kernel(const syg::FrameAr
 
         // ---------------- recombination + real split -> |X| or |X|^2 -> tile ----------------
         {
-            const int L = half * 32 + lane;                                                    // 0..63 within the frame's pair of warps
+            const int L = sub * 32 + lane;                                                     // lane within the frame's group of warps
             const float2* Zr[R];
             SYG_UNROLL
             for (int r = 0; r < R; ++r) Zr[r] = reinterpret_cast<const float2*>(freg + (size_t)r * ZF);
@@ -158,8 +192,8 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_big_kernel(const syg::FrameAr
                 return make_float2(c * (w.y - w.x), -c * (w.x + w.y));                         // aidx = 3: * (-1 - i)/sqrt2
             };
             SYG_UNROLL
-            for (int ii = 0; ii < 8; ++ii) {
-                const int q = L + 64 * ii;                                                     // 0..511
+            for (int ii = 0; ii < 512 / LPF; ++ii) {
+                const int q = L + LPF * ii;                                                    // 0..511
                 if (q == 0) continue;                                                          // residues 0 and 512: below
                 const int qm = MS - q;
                 const float2 w1 = __ldg(a.tw + q);                                            // W_M^q
