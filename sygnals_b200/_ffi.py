@@ -393,12 +393,16 @@ class Engine:
         self.lib.check(self.lib.dll.syg_ingest_pcm(self._h, raw_ptr, int(fmt), int(channels), int(n_frames), out_ptr, stream or None))
 
     def stft_host(self, y: np.ndarray, units: SygUnits, n_fft: int, hop: int, win_length: int, window: int = 0,
-                  center: bool = True, pad_mode: int = 0, out_kind: int = OUT_COMPLEX) -> np.ndarray:
+                  center: bool = True, pad_mode: int = 0, out_kind: int = OUT_COMPLEX, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``out``: optional preallocated result (e.g. ``pinned_empty``: the D2H copies then run at PCIe speed)."""
         y = _f32c(y)
         T = self.frame_count(units.unit_len, n_fft, hop, center)
         B = 1 + n_fft // 2
         dt = np.complex64 if out_kind == OUT_COMPLEX else np.float32
-        out = np.empty((units.n_units, B, T), dtype=dt)
+        if out is None:
+            out = np.empty((units.n_units, B, T), dtype=dt)
+        elif out.dtype != dt or out.shape != (units.n_units, B, T) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous array of shape (n_units, 1 + n_fft/2, T) and the output dtype")
         self.lib.check(self.lib.dll.syg_stft_host_f32(self._h, y.ctypes.data, C.byref(units), int(n_fft), int(hop),
                                                       int(win_length), int(window), int(bool(center)), int(pad_mode),
                                                       int(out_kind), out.ctypes.data))

@@ -252,33 +252,20 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_big_kernel(const syg::FrameAr
         __syncthreads();                                   // tile complete; the regions may be overwritten by the next round
 
         // ---------------- drain: rows of up to TT consecutive frames per bin ----------------
+        // (one thread per row with 16-byte stores was measured: 0.73 vs 0.68 ms at n_fft 4096 -- a warp then writes 32 half sectors
+        // per instruction instead of 4 full ones)
         {
-            const long long gf0 = round * TT;
-            const long long u0 = gf0 / a.T;
-            const int t0 = (int)(gf0 - u0 * a.T);
-            float* const obase = reinterpret_cast<float*>(a.stft_out) + (long long)u0 * B * a.T + t0;
-            if (t0 + TT <= a.T && gf0 + TT <= a.n_frames && (a.T & 3) == 0 && (TT & 3) == 0 && ((reinterpret_cast<uintptr_t>(obase) & 15u) == 0)) {
-                // the whole round lies in one unit and every row segment is 16-byte aligned: a thread takes whole rows, TT scalar
-                // reads from the (odd-pitch, conflict-free) tile and TT / 4 vector stores
-                for (int k = tid; k < B; k += NT) {
-                    const float* src = tile + k * TTP;
-                    float4* dst = reinterpret_cast<float4*>(obase + (long long)k * a.T);
-                    SYG_UNROLL
-                    for (int c = 0; c < TT / 4; ++c) dst[c] = make_float4(src[4 * c], src[4 * c + 1], src[4 * c + 2], src[4 * c + 3]);
-                }
-            } else {
-                constexpr int KS = NT / TT;
-                const int sl = tid % TT, kq = tid / TT;
-                const long long gfd = gf0 + sl;
-                if (gfd < a.n_frames) {
-                    const long long ud = gfd / a.T;
-                    const int td = (int)(gfd - ud * a.T);
-                    const float* src = tile + kq * TTP + sl;
-                    float* dst = reinterpret_cast<float*>(a.stft_out) + ((long long)ud * B + kq) * a.T + td;
-                    const long long dstep = (long long)KS * a.T;
-                    SYG_UNROLL_BY(4)
-                    for (int k = kq; k < B; k += KS, src += KS * TTP, dst += dstep) *dst = *src;
-                }
+            constexpr int KS = NT / TT;
+            const int sl = tid % TT, kq = tid / TT;
+            const long long gfd = round * TT + sl;
+            if (gfd < a.n_frames) {
+                const long long ud = gfd / a.T;
+                const int td = (int)(gfd - ud * a.T);
+                const float* src = tile + kq * TTP + sl;
+                float* dst = reinterpret_cast<float*>(a.stft_out) + ((long long)ud * B + kq) * a.T + td;
+                const long long dstep = (long long)KS * a.T;
+                SYG_UNROLL_BY(4)
+                for (int k = kq; k < B; k += KS, src += KS * TTP, dst += dstep) *dst = *src;
             }
         }
     }
