@@ -432,6 +432,35 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
             for (int i = 0; i < a.mel_nsweeps; ++i) a.mel_steps[i] = hv[1 + i];
         }
         a.n_mels = p->n_mels;
+        // Interval form of the projection (sygplan::MelIntervals) for the transforms with several frames per warp (n_fft <= 1024):
+        // O(bins) per lane instead of padded tap sweeps.  It overwrites the warp's |X|^2 with its running sums, so it is used when
+        // nothing after the mel stage reads the spectrum (no spectral contrast in the request).  SYGB200_MEL_IV=0 keeps the sweeps.
+        {
+            static int iv_env = -1;
+            if (iv_env < 0) { const char* e = std::getenv("SYGB200_MEL_IV"); iv_env = e ? std::atoi(e) : 1; }
+            if (iv_env && fl <= 1024 && fl >= 128 && !(mask & syg::FB_CONTRAST) && p->power == 2.0) {
+                std::string ki = key + ":iv", kin = key + ":ivn";
+                if (!ctx->host_ints.count(kin)) {
+                    sygplan::MelTable md;
+                    sygplan::MelIntervals iv;
+                    std::string err;
+                    const int E = fl >= 1024 ? 32 : (fl >= 256 ? 16 : 8);
+                    if (sygplan::build_mel((double)p->sr, fl, p->n_mels, (double)p->fmin, fmax, true, md, err))
+                        sygplan::build_mel_intervals((double)p->sr, fl, p->n_mels, (double)p->fmin, fmax, md, E, (fl / 2) / E, iv);
+                    if (iv.ok) {
+                        const float* d = nullptr;
+                        if ((rc = upload_table(ctx, ki, iv.blob, &d))) return rc;
+                    }
+                    ctx->host_ints[kin] = std::vector<int>{iv.ok ? iv.f4 : 0};
+                }
+                const int f4 = ctx->host_ints[kin][0];
+                if (f4 > 0) {
+                    a.mel_iv = 1;
+                    a.mel_pw = reinterpret_cast<const float*>(ctx->tables[ki]);
+                    a.mel_pw_f4 = f4;
+                }
+            }
+        }
         a.mel_power_is_2 = (p->power == 2.0);
         a.mel_half_power = (float)(0.5 * p->power);
         std::string dk = keyf("dct64:%d:%d:%d:%d:%.9g", p->n_mfcc, p->n_mels, p->dct_type, p->dct_ortho, (double)p->lifter);

@@ -594,6 +594,58 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             const float* pfr = pww + mf * RSS;
             const float4* const mw4 = t_melw;
             float fmx = 0.0f;
+            if (FW > 1 && a.mel_iv) {
+                // ---- interval form (sygplan::MelIntervals): lane (f, j) owns the E contiguous bins [jE, jE + E) of its frame.  Two
+                // running sums per bin -- the bin's weight in the filter rising through its mel interval and in the one falling
+                // through it -- restart at interval starts; their totals land in CR / CF (which take the place of |X|^2: nothing
+                // after this stage reads the spectrum in this mode) and every filter adds up its picks.
+                static_assert(FW == 1 || (E % 4 == 0 && E <= 32), "interval form: E bins per lane in one 32-bin block");
+                float* const reg = pww + mf * RSS;                      // this frame's region: |X|^2 now, CR [0, M) | CF [M, 2M) | zero
+                float p[E];
+                {
+                    const float4* pb4 = reinterpret_cast<const float4*>(reg + ppad(sl * E));
+                    SYG_UNROLL
+                    for (int i = 0; i < E / 4; ++i) {
+                        const float4 v = pb4[i];
+                        p[4 * i] = v.x; p[4 * i + 1] = v.y; p[4 * i + 2] = v.z; p[4 * i + 3] = v.w;
+                    }
+                }
+                __syncwarp();                                           // every lane holds its bins before the region is overwritten
+                const float4* const wt = mw4;                           // [E/2][G] {wr, wf, wr, wf}
+                const int4* const picks = reinterpret_cast<const int4*>(mw4 + M / 2);
+                const unsigned keep = reinterpret_cast<const unsigned*>(mw4 + M / 2 + 2 * a.n_mels)[sl];
+                float cr = 0.0f, cf = 0.0f;
+                float4* const cr4 = reinterpret_cast<float4*>(reg + sl * E);
+                float4* const cf4 = reinterpret_cast<float4*>(reg + M + sl * E);
+                SYG_UNROLL
+                for (int q = 0; q < E / 4; ++q) {
+                    float r[4], g[4];
+                    SYG_UNROLL
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 w = wt[(2 * q + h) * GS + sl];
+                        const int b = 4 * q + 2 * h;
+                        const bool k0 = (keep >> b) & 1u, k1 = (keep >> (b + 1)) & 1u;
+                        cr = __fmaf_rn(p[b], w.x, k0 ? cr : 0.0f);
+                        cf = __fmaf_rn(p[b], w.y, k0 ? cf : 0.0f);
+                        r[2 * h] = cr; g[2 * h] = cf;
+                        cr = __fmaf_rn(p[b + 1], w.z, k1 ? cr : 0.0f);
+                        cf = __fmaf_rn(p[b + 1], w.w, k1 ? cf : 0.0f);
+                        r[2 * h + 1] = cr; g[2 * h + 1] = cf;
+                    }
+                    cr4[q] = make_float4(r[0], r[1], r[2], r[3]);
+                    cf4[q] = make_float4(g[0], g[1], g[2], g[3]);
+                }
+                if (sl == 0) reg[2 * M] = 0.0f;                         // the slot unused picks point at
+                __syncwarp();
+                for (int m = sl; m < a.n_mels; m += GS) {
+                    const int4 pr = picks[2 * m], pq = picks[2 * m + 1];
+                    const float acc = ((reg[pr.x] + reg[pr.y]) + (reg[pr.z] + reg[pr.w])) + ((reg[pq.x] + reg[pq.y]) + (reg[pq.z] + reg[pq.w]));
+                    if (fvalid) {
+                        a.melws[gmf * a.n_mels + m] = acc;
+                        fmx = fmaxf(fmx, acc);
+                    }
+                }
+            } else
             if constexpr (SP::kMel && FW == 1) {
                 // plan-specialised sweeps: n_mels = 32 * n_sweeps, every trip count and tap offset is a constant
                 int goff = 0;

@@ -81,6 +81,7 @@ struct FrameArgs {
     float* cws;                 // [n_frames][2*nb]     contrast peaks | valleys (linear)
     unsigned* unit_max;         // [n_units][4]         bit images of max mel energy, max peak, max valley
     int mel_pw_f4;              // float4 count of mel_pw (for the shared-memory copy of the plan tables)
+    int mel_iv;                 // 1: mel_pw holds the interval-form blob (sygplan::MelIntervals) instead of sweep taps
     int mel_nsweeps;            // sweeps of the warp kernel's mel plan and their float4 step counts (host side: lets the launcher
     int mel_steps[8];           // pick a plan-specialised kernel); 0 sweeps = not recorded
     int variant;                // measurement switch (SYGB200_VARIANT, default 0): bit 0 = per-scheduler lock step (see frame_warp_kernel)

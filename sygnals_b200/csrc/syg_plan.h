@@ -122,6 +122,74 @@ inline bool build_mel(double sr, int n_fft, int n_mels, double fmin, double fmax
     return true;
 }
 
+// Mel projection in O(bins) per lane ("interval form", frame kernel with more than one frame per warp).  Slaney filters are
+// triangles over consecutive mel points f_0 < f_1 < ...: a bin between f_i and f_(i+1) feeds exactly two filters -- filter i with its
+// RISING weight and filter i-1 with its FALLING weight.  With the G lanes of a frame owning E contiguous bins each, the projection is
+// two running sums per bin (restarted at interval starts and at the lane's first bin) whose interval totals are then combined per
+// filter from a short pick list.  The weights are taken from the exact float32 filter table (MelTable::dense), so the result differs
+// from the tap sweep only in summation order.
+//   blob (float4 units): [0, M/2)            {wr(2i), wf(2i), wr(2i+1), wf(2i+1)} of lane j at index i*G + j   (M = G*E bins)
+//                        [M/2, M/2 + 2 n)     per filter two int4: pick indices into CR (bins, 0..M-1) / CF (M + bin); unused -> 2M (a zero)
+//                        [.., + ceil(G/4))    per lane one uint: bit b set = bin b of the lane continues its predecessor's interval
+struct MelIntervals { bool ok = false; std::vector<float> blob; int f4 = 0; };
+
+inline void build_mel_intervals(double sr, int n_fft, int n_mels, double fmin, double fmax, const MelTable& t, int E, int G,
+                                MelIntervals& out) {
+    out.ok = false;
+    const int M = n_fft / 2, B = M + 1;
+    if (G * E != M || t.dense.size() != (size_t)n_mels * B || E > 32 || (E & 3)) return;
+    if (fmax <= 0) fmax = sr / 2.0;
+    const int n = n_mels + 2;
+    const double mn = hz_to_mel(fmin), mx = hz_to_mel(fmax), lstep = (mx - mn) / (double)(n - 1), step_hz = bin_hz(sr, n_fft);
+    std::vector<double> mel_f(n);
+    for (int i = 0; i < n; ++i) mel_f[i] = mel_to_hz(i == n - 1 ? mx : mn + lstep * (double)i);
+    std::vector<int> iv(M);                                     // interval of bin k: largest i with mel_f[i] <= f_k (-1: below fmin)
+    for (int k = 0; k < M; ++k) {
+        const double fk = (double)k * step_hz;
+        int i = -1;
+        while (i + 1 < n && mel_f[i + 1] <= fk) ++i;
+        iv[k] = i;
+    }
+    auto rise = [&](int k) { return (iv[k] >= 0 && iv[k] <= n_mels - 1) ? iv[k] : -1; };
+    auto fall = [&](int k) { return (iv[k] - 1 >= 0 && iv[k] - 1 <= n_mels - 1) ? iv[k] - 1 : -1; };
+    // the model must reproduce the filter table exactly: every non-zero weight belongs to the bin's rise or fall filter
+    for (int m = 0; m < n_mels; ++m) {
+        if (t.dense[(size_t)m * B + M] != 0.0f) return;         // Nyquist bin: never weighted (fmax <= sr/2)
+        for (int k = 0; k < M; ++k)
+            if (t.dense[(size_t)m * B + k] != 0.0f && m != rise(k) && m != fall(k)) return;
+    }
+    const int f4_w = M / 2, f4_p = 2 * n_mels, f4_k = (G + 3) / 4;
+    out.f4 = f4_w + f4_p + f4_k;
+    out.blob.assign((size_t)out.f4 * 4, 0.0f);
+    for (int j = 0; j < G; ++j)
+        for (int b = 0; b < E; ++b) {
+            const int k = j * E + b;
+            const float wr = rise(k) >= 0 ? t.dense[(size_t)rise(k) * B + k] : 0.0f;
+            const float wf = fall(k) >= 0 ? t.dense[(size_t)fall(k) * B + k] : 0.0f;
+            float* q = &out.blob[((size_t)(b / 2) * G + j) * 4 + (b & 1) * 2];
+            q[0] = wr; q[1] = wf;
+        }
+    int* picks = reinterpret_cast<int*>(&out.blob[(size_t)f4_w * 4]);
+    for (int m = 0; m < n_mels; ++m) {
+        int nr = 0, nf = 0;
+        int* pr = picks + (size_t)m * 8;
+        for (int q = 0; q < 8; ++q) pr[q] = 2 * M;
+        for (int k = 0; k < M; ++k) {
+            const bool lane_end = (k % E) == E - 1;
+            if (rise(k) == m && (lane_end || k == M - 1 || iv[k + 1] != iv[k])) { if (nr == 4) return; pr[nr++] = k; }
+            if (fall(k) == m && (lane_end || k == M - 1 || iv[k + 1] != iv[k])) { if (nf == 4) return; pr[4 + nf++] = M + k; }
+        }
+    }
+    unsigned* keep = reinterpret_cast<unsigned*>(&out.blob[(size_t)(f4_w + f4_p) * 4]);
+    for (int j = 0; j < G; ++j) {
+        unsigned bits = 0;
+        for (int b = 1; b < E; ++b)
+            if (iv[j * E + b] == iv[j * E + b - 1]) bits |= 1u << b;
+        keep[j] = bits;
+    }
+    out.ok = true;
+}
+
 // Mel filters re-expressed for the warp kernel: "slots" sorted by span (longest first, so the 32 lanes of a warp
 // sweep filters of similar length), taps indexed in the PADDED power-spectrum space (padi(k) = k + k/32, a zero
 // weight at every pad position) and padded to a multiple of 4 taps.  desc = {filter m, padded start, taps, offset}.
