@@ -38,7 +38,10 @@ struct WarpTile {
     // its pairs into registers) as the |X|^2 spectrum.  Halves the shared memory per warp, which the SM hands to L1.
     // With FW > 1 the lane groups of a warp store their |X|^2 in the same 32-bit shared-memory access: regions start G banks apart
     // (pitch = G mod 32) so that the groups never collide.
-    static constexpr int RS0 = ((2 * ZS > PS ? 2 * ZS : PS) + 3) / 4 * 4;
+    // with several frames per warp the region also holds the two padded running-sum arrays of the interval-form mel projection
+    static constexpr int IVW = (FW > 1 && M % 32 == 0) ? 2 * (M + M / 8) + 4 : 0;
+    static constexpr int RS1 = (2 * ZS > PS ? 2 * ZS : PS);
+    static constexpr int RS0 = ((RS1 > IVW ? RS1 : IVW) + 3) / 4 * 4;
     static constexpr int RS = (FW == 1) ? RS0 : ((RS0 - G + 31) / 32 * 32 + G);
     static constexpr int warp_floats = FW * RS;
     static constexpr size_t bytes = (size_t)kWarps * warp_floats * sizeof(float);
@@ -600,7 +603,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 // through it -- restart at interval starts; their totals land in CR / CF (which take the place of |X|^2: nothing
                 // after this stage reads the spectrum in this mode) and every filter adds up its picks.
                 static_assert(FW == 1 || (E % 4 == 0 && E <= 32), "interval form: E bins per lane in one 32-bin block");
-                float* const reg = pww + mf * RSS;                      // this frame's region: |X|^2 now, CR [0, M) | CF [M, 2M) | zero
+                float* const reg = pww + mf * RSS;                      // this frame's region: |X|^2 now, then CR | CF | zero word
                 float p[E];
                 {
                     const float4* pb4 = reinterpret_cast<const float4*>(reg + ppad(sl * E));
@@ -613,10 +616,11 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 __syncwarp();                                           // every lane holds its bins before the region is overwritten
                 const float4* const wt = mw4;                           // [E/2][G] {wr, wf, wr, wf}
                 const int4* const picks = reinterpret_cast<const int4*>(mw4 + M / 2);
-                const unsigned keep = reinterpret_cast<const unsigned*>(mw4 + M / 2 + 2 * a.n_mels)[sl];
+                const unsigned keep = reinterpret_cast<const unsigned*>(mw4 + M / 2 + a.n_mels)[sl];
+                constexpr int PSM = M + M / 8;                          // CR at [0, PSM), CF at [PSM, 2 PSM), both in the padded bin layout
                 float cr = 0.0f, cf = 0.0f;
-                float4* const cr4 = reinterpret_cast<float4*>(reg + sl * E);
-                float4* const cf4 = reinterpret_cast<float4*>(reg + M + sl * E);
+                float4* const cr4 = reinterpret_cast<float4*>(reg + ppad(sl * E));
+                float4* const cf4 = reinterpret_cast<float4*>(reg + PSM + ppad(sl * E));
                 SYG_UNROLL
                 for (int q = 0; q < E / 4; ++q) {
                     float r[4], g[4];
@@ -635,11 +639,11 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     cr4[q] = make_float4(r[0], r[1], r[2], r[3]);
                     cf4[q] = make_float4(g[0], g[1], g[2], g[3]);
                 }
-                if (sl == 0) reg[2 * M] = 0.0f;                         // the slot unused picks point at
+                if (sl == 0) reg[2 * PSM] = 0.0f;                       // the word unused picks point at
                 __syncwarp();
                 for (int m = sl; m < a.n_mels; m += GS) {
-                    const int4 pr = picks[2 * m], pq = picks[2 * m + 1];
-                    const float acc = ((reg[pr.x] + reg[pr.y]) + (reg[pr.z] + reg[pr.w])) + ((reg[pq.x] + reg[pq.y]) + (reg[pq.z] + reg[pq.w]));
+                    const int4 pk4 = picks[m];                          // {r0, r1, f0, f1}
+                    const float acc = (reg[pk4.x] + reg[pk4.y]) + (reg[pk4.z] + reg[pk4.w]);
                     if (fvalid) {
                         a.melws[gmf * a.n_mels + m] = acc;
                         fmx = fmaxf(fmx, acc);

@@ -129,7 +129,9 @@ inline bool build_mel(double sr, int n_fft, int n_mels, double fmin, double fmax
 // filter from a short pick list.  The weights are taken from the exact float32 filter table (MelTable::dense), so the result differs
 // from the tap sweep only in summation order.
 //   blob (float4 units): [0, M/2)            {wr(2i), wf(2i), wr(2i+1), wf(2i+1)} of lane j at index i*G + j   (M = G*E bins)
-//                        [M/2, M/2 + 2 n)     per filter two int4: pick indices into CR (bins, 0..M-1) / CF (M + bin); unused -> 2M (a zero)
+//                        [M/2, M/2 + n)       per filter one int4 {r0, r1, f0, f1}: word indices of its (at most two) rise totals in CR
+//                                             and fall totals in CF; both arrays use the padded spectrum layout k + 4 (k / 32), CF
+//                                             starts PSM = M + M/8 words after CR; unused picks point at word 2 PSM (kept zero)
 //                        [.., + ceil(G/4))    per lane one uint: bit b set = bin b of the lane continues its predecessor's interval
 struct MelIntervals { bool ok = false; std::vector<float> blob; int f4 = 0; };
 
@@ -158,7 +160,10 @@ inline void build_mel_intervals(double sr, int n_fft, int n_mels, double fmin, d
         for (int k = 0; k < M; ++k)
             if (t.dense[(size_t)m * B + k] != 0.0f && m != rise(k) && m != fall(k)) return;
     }
-    const int f4_w = M / 2, f4_p = 2 * n_mels, f4_k = (G + 3) / 4;
+    const int f4_w = M / 2, f4_p = n_mels, f4_k = (G + 3) / 4;
+    if (M % 32) return;
+    const int PSM = M + M / 8;                                  // padded length of CR (and of CF)
+    auto pad = [](int k) { return k + ((k >> 5) << 2); };
     out.f4 = f4_w + f4_p + f4_k;
     out.blob.assign((size_t)out.f4 * 4, 0.0f);
     for (int j = 0; j < G; ++j)
@@ -172,12 +177,12 @@ inline void build_mel_intervals(double sr, int n_fft, int n_mels, double fmin, d
     int* picks = reinterpret_cast<int*>(&out.blob[(size_t)f4_w * 4]);
     for (int m = 0; m < n_mels; ++m) {
         int nr = 0, nf = 0;
-        int* pr = picks + (size_t)m * 8;
-        for (int q = 0; q < 8; ++q) pr[q] = 2 * M;
+        int* pr = picks + (size_t)m * 4;
+        for (int q = 0; q < 4; ++q) pr[q] = 2 * PSM;
         for (int k = 0; k < M; ++k) {
             const bool lane_end = (k % E) == E - 1;
-            if (rise(k) == m && (lane_end || k == M - 1 || iv[k + 1] != iv[k])) { if (nr == 4) return; pr[nr++] = k; }
-            if (fall(k) == m && (lane_end || k == M - 1 || iv[k + 1] != iv[k])) { if (nf == 4) return; pr[4 + nf++] = M + k; }
+            if (rise(k) == m && (lane_end || k == M - 1 || iv[k + 1] != iv[k])) { if (nr == 2) return; pr[nr++] = pad(k); }
+            if (fall(k) == m && (lane_end || k == M - 1 || iv[k + 1] != iv[k])) { if (nf == 2) return; pr[2 + nf++] = PSM + pad(k); }
         }
     }
     unsigned* keep = reinterpret_cast<unsigned*>(&out.blob[(size_t)(f4_w + f4_p) * 4]);
