@@ -432,19 +432,19 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
             for (int i = 0; i < a.mel_nsweeps; ++i) a.mel_steps[i] = hv[1 + i];
         }
         a.n_mels = p->n_mels;
-        // Interval form of the projection (sygplan::MelIntervals) for the transforms with several frames per warp (n_fft <= 1024):
-        // O(bins) per lane instead of padded tap sweeps.  It overwrites the warp's |X|^2 with its running sums, so it is used when
-        // nothing after the mel stage reads the spectrum (no spectral contrast in the request).  SYGB200_MEL_IV=0 keeps the sweeps.
+        // Interval form of the projection (sygplan::MelIntervals): O(bins) per lane instead of padded tap sweeps.  Default for the
+        // transforms with several frames per warp (n_fft <= 1024); SYGB200_MEL_IV=0 keeps the sweeps, =2 also takes n_fft 2048.
         {
             static int iv_env = -1;
             if (iv_env < 0) { const char* e = std::getenv("SYGB200_MEL_IV"); iv_env = e ? std::atoi(e) : 1; }
-            if (iv_env && fl <= 1024 && fl >= 128 && !(mask & syg::FB_CONTRAST) && p->power == 2.0) {
+            // (the frame kernel runs spectral contrast BEFORE the mel stage, so overwriting the spectrum there is safe)
+            if (iv_env && fl <= ((iv_env >= 2) ? 2048 : 1024) && fl >= 128 && p->power == 2.0) {
                 std::string ki = key + ":iv", kin = key + ":ivn";
                 if (!ctx->host_ints.count(kin)) {
                     sygplan::MelTable md;
                     sygplan::MelIntervals iv;
                     std::string err;
-                    const int E = fl >= 1024 ? 32 : (fl >= 256 ? 16 : 8);
+                    const int E = fl >= 1024 ? 32 : (fl >= 256 ? 16 : 8);     // = WarpTile::E of the kernel instantiation for this n_fft
                     if (sygplan::build_mel((double)p->sr, fl, p->n_mels, (double)p->fmin, fmax, true, md, err))
                         sygplan::build_mel_intervals((double)p->sr, fl, p->n_mels, (double)p->fmin, fmax, md, E, (fl / 2) / E, iv);
                     if (iv.ok) {

@@ -38,8 +38,8 @@ struct WarpTile {
     // its pairs into registers) as the |X|^2 spectrum.  Halves the shared memory per warp, which the SM hands to L1.
     // With FW > 1 the lane groups of a warp store their |X|^2 in the same 32-bit shared-memory access: regions start G banks apart
     // (pitch = G mod 32) so that the groups never collide.
-    // with several frames per warp the region also holds the two padded running-sum arrays of the interval-form mel projection
-    static constexpr int IVW = (FW > 1 && M % 32 == 0) ? 2 * (M + M / 8) + 4 : 0;
+    // the region also holds the two padded running-sum arrays of the interval-form mel projection
+    static constexpr int IVW = (M % 32 == 0) ? 2 * (M + M / 8) + 4 : 0;
     static constexpr int RS1 = (2 * ZS > PS ? 2 * ZS : PS);
     static constexpr int RS0 = ((RS1 > IVW ? RS1 : IVW) + 3) / 4 * 4;
     static constexpr int RS = (FW == 1) ? RS0 : ((RS0 - G + 31) / 32 * 32 + G);
@@ -586,6 +586,44 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             }
         }
 
+        // ---------------- spectral contrast: per band mean of the n largest / n smallest magnitudes ----------------
+        if (a.mask & syg::FB_CONTRAST) {
+            for (int ff = 0; ff < FW; ++ff) {
+                const long long gff = task * FW + ff;
+                if (gff >= a.n_frames) break;
+                const float* pp = pww + ff * RSS;
+                float pmx = 0.0f, vmx = 0.0f;
+                float mine_pv = 0.0f;                                   // lane bd keeps band bd's peak, lane nb + bd its valley
+                const int lane_v = lane - a.nb;
+                if constexpr (SP::kBands) {
+                    SYG_UNROLL
+                    for (int bd = 0; bd < SP::nb; ++bd) {               // compile-time band layout: (lo, count, n) fold into the code
+                        const float2 pv = band_peak_valley_stream<true>(pp, SP::band(bd, 0), SP::band(bd, 1), SP::band(bd, 2));
+                        mine_pv = (lane == bd) ? pv.x : mine_pv;
+                        mine_pv = (lane == SP::nb + bd) ? pv.y : mine_pv;
+                        pmx = fmaxf(pmx, pv.x);
+                        vmx = fmaxf(vmx, pv.y);
+                    }
+                } else
+                for (int bd = 0; bd < a.nb; ++bd) {
+                    const int cnt = a.band_cnt[bd];                     // 1 <= band_n <= band_cnt is guaranteed by the plan (syg_api.cu)
+                    float2 pv = make_float2(__uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u));   // empty band: mean of nothing -> NaN (numpy)
+                    if (cnt > 0) pv = band_peak_valley_stream<false>(pp, a.band_lo[bd], cnt, a.band_n[bd]);
+                    mine_pv = (lane == bd) ? pv.x : mine_pv;
+                    mine_pv = (lane_v == bd) ? pv.y : mine_pv;
+                    pmx = fmaxf(pmx, pv.x);                             // fmaxf drops the NaN of an empty band
+                    vmx = fmaxf(vmx, pv.y);
+                }
+                if (lane < 2 * a.nb) a.cws[gff * (2 * a.nb) + lane] = mine_pv;   // one coalesced store per frame (nb <= kMaxBands = 12)
+                const long long uff = __shfl_sync(kFull, u, ff * G);    // unit of frame ff (all lanes take part)
+                if (lane == 0) {
+                    unsigned* um = a.unit_max + uff * 4;
+                    if (pmx > 0.0f) atomicMax(&um[1], __float_as_uint(pmx));
+                    if (vmx > 0.0f) atomicMax(&um[2], __float_as_uint(vmx));
+                }
+            }
+        }
+        __syncwarp();                                                   // interval-form mel overwrites the spectrum: contrast has read it
         // ---------------- mel energies: one filter per lane; the warp sweeps GS = 32 / FW filters of each of its frames at once ----------------
         // (Loading a tap vector once for all FW frames of the task -- 32 filters per sweep, frames in an inner loop -- was measured:
         // fewer shared-memory wavefronts but 7 instead of 4 instructions per step and idle lanes in the last sweep; cfg3 +10 % time.)
@@ -597,12 +635,12 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             const float* pfr = pww + mf * RSS;
             const float4* const mw4 = t_melw;
             float fmx = 0.0f;
-            if (FW > 1 && a.mel_iv) {
+            if (a.mel_iv) {
                 // ---- interval form (sygplan::MelIntervals): lane (f, j) owns the E contiguous bins [jE, jE + E) of its frame.  Two
                 // running sums per bin -- the bin's weight in the filter rising through its mel interval and in the one falling
                 // through it -- restart at interval starts; their totals land in CR / CF (which take the place of |X|^2: nothing
                 // after this stage reads the spectrum in this mode) and every filter adds up its picks.
-                static_assert(FW == 1 || (E % 4 == 0 && E <= 32), "interval form: E bins per lane in one 32-bin block");
+                static_assert(E % 4 == 0 && E <= 32, "interval form: E bins per lane in one 32-bin block");
                 float* const reg = pww + mf * RSS;                      // this frame's region: |X|^2 now, then CR | CF | zero word
                 float p[E];
                 {
@@ -725,43 +763,6 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             if (sl == 0 && fvalid && gmx > 0.0f) atomicMax(&a.unit_max[umf * 4 + 0], __float_as_uint(gmx));
         }
 
-        // ---------------- spectral contrast: per band mean of the n largest / n smallest magnitudes ----------------
-        if (a.mask & syg::FB_CONTRAST) {
-            for (int ff = 0; ff < FW; ++ff) {
-                const long long gff = task * FW + ff;
-                if (gff >= a.n_frames) break;
-                const float* pp = pww + ff * RSS;
-                float pmx = 0.0f, vmx = 0.0f;
-                float mine_pv = 0.0f;                                   // lane bd keeps band bd's peak, lane nb + bd its valley
-                const int lane_v = lane - a.nb;
-                if constexpr (SP::kBands) {
-                    SYG_UNROLL
-                    for (int bd = 0; bd < SP::nb; ++bd) {               // compile-time band layout: (lo, count, n) fold into the code
-                        const float2 pv = band_peak_valley_stream<true>(pp, SP::band(bd, 0), SP::band(bd, 1), SP::band(bd, 2));
-                        mine_pv = (lane == bd) ? pv.x : mine_pv;
-                        mine_pv = (lane == SP::nb + bd) ? pv.y : mine_pv;
-                        pmx = fmaxf(pmx, pv.x);
-                        vmx = fmaxf(vmx, pv.y);
-                    }
-                } else
-                for (int bd = 0; bd < a.nb; ++bd) {
-                    const int cnt = a.band_cnt[bd];                     // 1 <= band_n <= band_cnt is guaranteed by the plan (syg_api.cu)
-                    float2 pv = make_float2(__uint_as_float(0x7fc00000u), __uint_as_float(0x7fc00000u));   // empty band: mean of nothing -> NaN (numpy)
-                    if (cnt > 0) pv = band_peak_valley_stream<false>(pp, a.band_lo[bd], cnt, a.band_n[bd]);
-                    mine_pv = (lane == bd) ? pv.x : mine_pv;
-                    mine_pv = (lane_v == bd) ? pv.y : mine_pv;
-                    pmx = fmaxf(pmx, pv.x);                             // fmaxf drops the NaN of an empty band
-                    vmx = fmaxf(vmx, pv.y);
-                }
-                if (lane < 2 * a.nb) a.cws[gff * (2 * a.nb) + lane] = mine_pv;   // one coalesced store per frame (nb <= kMaxBands = 12)
-                const long long uff = __shfl_sync(kFull, u, ff * G);    // unit of frame ff (all lanes take part)
-                if (lane == 0) {
-                    unsigned* um = a.unit_max + uff * 4;
-                    if (pmx > 0.0f) atomicMax(&um[1], __float_as_uint(pmx));
-                    if (vmx > 0.0f) atomicMax(&um[2], __float_as_uint(vmx));
-                }
-            }
-        }
         __syncwarp();                                                   // smem slices are reused by the next task
     }
 }

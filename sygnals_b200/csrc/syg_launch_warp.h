@@ -52,7 +52,7 @@ static bool spec_matches(const syg::FrameArgs& a) {
         for (int i = 0; i < SP::nb; ++i)
             if (a.band_lo[i] != SP::band(i, 0) || a.band_cnt[i] != SP::band(i, 1) || a.band_n[i] != SP::band(i, 2)) return false;
     }
-    if (a.mask & syg::FB_MFCC) {
+    if ((a.mask & syg::FB_MFCC) && !a.mel_iv) {
         if (!SP::kMel || !a.mel_power_is_2 || a.n_mels != 32 * SP::n_sweeps || a.mel_nsweeps != SP::n_sweeps) return false;
         for (int i = 0; i < SP::n_sweeps; ++i)
             if (a.mel_steps[i] != SP::steps(i)) return false;
