@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
             tbw[i] = __ldg(reinterpret_cast<const float2*>(a.window) + i);
             tbw[M + i] = __ldg(a.tw + i);
         }
-        for (int i = tid; i <= M / 2; i += NT) tbw[2 * M + i] = __ldg(a.tws + i);
+        for (int i = tid; i <= M / 2; i += NT) {                        // split twiddles with the halving folded in (split_power)
+            const float2 w = __ldg(a.tws + i);
+            tbw[2 * M + i] = make_float2(0.5f * w.x, 0.5f * w.y);
+        }
         __syncthreads();
     }
     const bool full = (a.nperseg == 2 * M);
@@ -176,14 +179,15 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                     const bool blk = ((M - kk) & (E - 1)) == 0;
                     float2 zm = blk ? zm1[c1] : zm0[c1];
                     if (i == 0 && j == 0) zm = zk;
-                    const float2 w = TBLW ? t_tws[k] : __ldg(&t_tws[k]);
-                    float xkr, xki, xmr, xmi;
-                    real_split(zk.x, zk.y, zm.x, zm.y, w.x, w.y, xkr, xki, xmr, xmi);
+                    float2 w = TBLW ? t_tws[k] : __ldg(&t_tws[k]);
+                    if (!TBLW) w = make_float2(0.5f * w.x, 0.5f * w.y);
+                    float pwk, pwm;
+                    split_power(zk, zm, w, pwk, pwm);                  // |X[k]|^2, |X[M-k]|^2 straight from the packed pair (14 instead of 22 operations)
                     if (valid) {
-                        pk0[kk + ((kk >> 5) << 2)] += __fmaf_rn(xkr, xkr, xki * xki);
+                        pk0[kk + ((kk >> 5) << 2)] += pwk;
                         const int q1 = (M - kk) + (((M - kk - 1) >> 5) << 2);
                         const bool blk5 = ((M - kk) & 31) == 0;
-                        if (2 * k != M) (blk5 ? pm1 : pm0)[q1] += __fmaf_rn(xmr, xmr, xmi * xmi);
+                        if (2 * k != M) (blk5 ? pm1 : pm0)[q1] += pwm;
                     }
                 }
             }
