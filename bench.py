@@ -176,7 +176,10 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi polled every 50 ms from before the warm-up to after the timed region; `stop(t0, t1)` keeps the samples whose
+    timestamps fall inside the timed window [t0, t1] (wall clock) and, when the window is shorter than the polling interval (strong
+    scaling at 8 GPUs: 10 steps take 44 ms), the samples taken under the same load since the warm-up began."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index = index
@@ -184,40 +187,56 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                       "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.t_start = time.time()
+            self.lines = []
+            import threading
+            self.th = threading.Thread(target=lambda: [self.lines.append(ln) for ln in self.p.stdout], daemon=True)
+            self.th.start()
         except Exception:
             self.p = None
 
-    def stop(self):
+    def count(self) -> int:
+        return len(self.lines) if self.p else 1 << 30
+
+    def stop(self, t0=None, t1=None):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.p.terminate()
         try:
-            out, _ = self.p.communicate(timeout=5)
+            self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
-            out = ""
-        sm, mx, reasons, pw = [], [], set(), []
-        for ln in out.strip().splitlines():
+        self.th.join(timeout=2)
+        import datetime
+        rows = []
+        for ln in list(self.lines):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), [v.lower().startswith("active") for v in f[4:8]]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # median over the upper half of the samples (the sampler also sees the idle edges of the region)
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:]
-        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max(pw)}
+        window = [r for r in rows if t0 is not None and t0 - 0.03 <= r[0] <= t1 + 0.03]
+        scope = "timed region"
+        if len(window) < 2:                                            # shorter than the polling interval: same load since the warm-up
+            window = [r for r in rows if t0 is None or r[0] <= (t1 or r[0]) + 0.03]
+            scope = "warm-up + timed region (the timed region is shorter than the 50 ms polling interval)"
+        reasons = set()
+        for r in window:
+            for name, on in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if on:
+                    reasons.add(name)
+        sm_sorted = sorted(r[1] for r in window)
+        load = sm_sorted[len(sm_sorted) // 2:]                         # upper half: the sampler also sees idle edges
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(r[2] for r in window), "reasons": sorted(reasons),
+                "samples": len(window), "power_w_max": max(r[3] for r in window), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------------ native arm
@@ -265,22 +284,34 @@ class Ctx:
         """W untimed steps, then `steps` steps between CUDA events on the current stream, barrier + synchronize on both sides.
         Returns (max-over-ranks ms for all steps, this rank's ms, clocks, profile dict)."""
         torch = self.torch
+        clocks = ClockSampler(self.local) if sample_clocks else None
+        if clocks:
+            clocks.start()                                             # polling runs through warm-up and timed region
         for _ in range(self.warm if warm is None else warm):
             step()
+        if clocks:
+            # short steps (strong scaling at 8 GPUs: 4.4 ms): keep the same load up, untimed, until the poller has delivered its
+            # first samples, so that the clock record covers the load the timed steps run under (bounded: 2 s); the number of
+            # extra steps is agreed across ranks (collectives inside `step` must match)
+            t_w = time.time()
+            while True:
+                more = 1.0 if (clocks.count() < 3 and time.time() - t_w < 2.0) else 0.0
+                if self.max_over_ranks(more) == 0.0:
+                    break
+                step()
         torch.cuda.synchronize()
         self.eng.profile_read(reset=True)
         self.eng.profile_enable(True)
-        clocks = ClockSampler(self.local) if sample_clocks else None
         self.barrier()
-        if clocks:
-            clocks.start()
+        t0w = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             step()
         e1.record()
         self.barrier()
-        clk = clocks.stop() if clocks else None
+        t1w = time.time()
+        clk = clocks.stop(t0w, t1w) if clocks else None
         ms = e0.elapsed_time(e1)
         prof = self.eng.profile_read(reset=True)
         self.eng.profile_enable(False)
