@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the Sygnals segment->features hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg3|cfg2|cfg5] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg1|cfg2|cfg3|cfg5] [--impl native|reference]
 
 Default workload = BASELINE.json configs[3] ("cfg4", the config the metric "audio-sec/sec (MFCC+spectral feats)" names):
 ONE 10 h synthetic 44.1 kHz recording, fixed-length 2 s segments with 50 % overlap (36 000 segments), per segment
@@ -42,6 +42,10 @@ WORKLOADS = {
                  desc="env-sound: ONE 10 h @ 44.1 kHz recording, 2 s segments, 50% overlap, MFCC13+contrast7+centroid+rolloff+rms+crest, "
                       "n_fft 2048 hop 512, mean over each segment's frames",
                  sr=44100, seg_sec=2.0, overlap=0.5, hours=10.0, features=CFG4_FEATURES, fl=2048, hop=512, fp=None),
+    "cfg1": dict(kind="clips", metric="audio-sec/sec (MFCC+RMS, one clip per call)", unit="audio-s/s",
+                 desc="the reference's CPU case: ONE 10 s @ 22.05 kHz clip per call, MFCC20 (n_fft 2048, hop 512, 128 mels) + RMS",
+                 sr=22050, clip=220500, n_clips=1, features=["mfcc", "rms_energy"], fl=2048, hop=512,
+                 fp={"mfcc": {"n_mels": 128, "n_mfcc": 20}}),
     "cfg3": dict(kind="clips", metric="audio-sec/sec (MFCC)", unit="audio-s/s",
                  desc="speech-commands: 100k x 1 s @ 16 kHz clips, MFCC13, n_fft 512 hop 160, 40 mels",
                  sr=16000, clip=16000, n_clips=100000, features=["mfcc"], fl=512, hop=160, fp={"mfcc": {"n_mels": 40}}),
@@ -120,7 +124,7 @@ def cpu_reference_run(workload: str, n_units: int, steps: int, warmup: int, proc
         what = f"{n_units} x {w['seg_sec']} s segments per step through oracle.extract_features + format_feature_vectors_per_segment"
     elif kind in ("clips", "stft"):
         units = list(synth.clip_batch(n_units, w["clip"], sr, seed=99, edges=False))
-        what = f"{n_units} x 1 s clips per step through oracle." + ("extract_features" if kind == "clips" else "compute_stft (6 sizes)")
+        what = f"{n_units} x {w['clip'] / sr:g} s clips per step through oracle." + ("extract_features" if kind == "clips" else "compute_stft (6 sizes)")
     else:
         units = [synth.long_signal(sr, sr, seed=700 + i, block_sec=0.25) for i in range(n_units)]
         what = f"{n_units} channel-seconds per step through oracle.compute_psd_welch + rms + crest_factor"
@@ -142,7 +146,9 @@ def cpu_reference_run(workload: str, n_units: int, steps: int, warmup: int, proc
 
 def unit_seconds(w) -> float:
     """unique audio (channel) seconds one unit stands for"""
-    return w["seg_sec"] * (1.0 - w["overlap"]) if w["kind"] == "segments" else 1.0
+    if w["kind"] == "segments":
+        return w["seg_sec"] * (1.0 - w["overlap"])
+    return w["clip"] / float(w["sr"]) if "clip" in w else 1.0
 
 
 def run_reference(args):
@@ -536,9 +542,10 @@ def run_clips(c: Ctx):
     from sygnals_b200 import _ffi
     from sygnals_b200.utils import synth
     torch, args, eng = c.torch, c.args, c.eng
-    w = WORKLOADS["cfg3"]
+    w = WORKLOADS[args.workload]
     sr, L = w["sr"], w["clip"]
     n_all = args.units or w["n_clips"]
+    clip_s = L / float(sr)                                                # audio seconds per clip
     u0, u1 = shard(n_all, c.rank, c.world)
     n = u1 - u0
     counts = [shard(n_all, r, c.world)[1] - shard(n_all, r, c.world)[0] for r in range(c.world)]
@@ -556,9 +563,23 @@ def run_clips(c: Ctx):
         state["full"] = gather_block(c, out, counts)
 
     ms_max, ms, clk, prof = c.time_device(step, args.steps)
-    value = n_all * args.steps / (ms_max * 1e-3)
+    value = n_all * clip_s * args.steps / (ms_max * 1e-3)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.workload == "cfg1":
+        # the call a Sygnals user makes: extract_features(y float64, ...) -> DataFrame (H2D, kernels, D2H, float64 columns, pandas)
+        import numpy as np
+        from sygnals_b200.core.features import manager
+        y64 = y[0].cpu().numpy().astype(np.float64)
+        ne = max(3, args.e2e_steps)
+        manager.extract_features(y64, sr, w["features"], frame_length=w["fl"], hop_length=w["hop"], feature_params=w["fp"])
+        t0 = time.perf_counter()
+        for _ in range(ne):
+            df = manager.extract_features(y64, sr, w["features"], frame_length=w["fl"], hop_length=w["hop"], feature_params=w["fp"])
+        dt = (time.perf_counter() - t0)
+        e2e = {"value": clip_s * ne / dt, "unit": w["unit"], "h2d_bytes_per_step": int(L * 4), "d2h_bytes_per_step": int(out.numel() * 4),
+               "steps": ne, "ms_per_step": 1e3 * dt / ne, "api": "sygnals_b200.core.features.manager.extract_features -> DataFrame",
+               "columns": int(df.shape[1]), "frames": int(df.shape[0])}
+    elif not args.no_e2e:
         # the clips as 16-bit PCM (what the dataset's WAV files hold) in pinned memory -> features in pinned memory
         y16 = torch.empty((n, L), dtype=torch.int16, pin_memory=True)
         y16.copy_((y * 32767.0).round().clamp(-32768, 32767).to(torch.int16))
@@ -570,14 +591,14 @@ def run_clips(c: Ctx):
         chk = torch.empty_like(out)
         eng.features_dev(yq.data_ptr(), units, p, chk.data_ptr(), stream)
         same = bool(torch.equal(oh.to(c.dev), chk))
-        e2e = {"value": n_all * ne / dt, "unit": w["unit"], "h2d_bytes_per_step": int(c.sum_over_ranks(float(n * L * 2))),
+        e2e = {"value": n_all * clip_s * ne / dt, "unit": w["unit"], "h2d_bytes_per_step": int(c.sum_over_ranks(float(n * L * 2))),
                "d2h_bytes_per_step": int(c.sum_over_ranks(float(out.numel() * 4))), "steps": ne, "ms_per_step": 1e3 * dt / ne,
                "input": "16-bit PCM clips in pinned host memory", "matches_device_path": same}
         del yq, chk, y16
         yh = torch.empty((n, L), dtype=torch.float32, pin_memory=True)
         yh.copy_(y)
         dt32 = c.time_wall(lambda: eng.features_host(None, units, p, out=oh_np, y_ptr=yh.data_ptr()), ne)
-        e2e["f32"] = {"value": n_all * ne / dt32, "unit": w["unit"], "h2d_bytes_per_step": int(c.sum_over_ranks(float(n * L * 4))),
+        e2e["f32"] = {"value": n_all * clip_s * ne / dt32, "unit": w["unit"], "h2d_bytes_per_step": int(c.sum_over_ranks(float(n * L * 4))),
                       "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "ms_per_step": 1e3 * dt32 / ne,
                       "matches_device_path": bool(torch.equal(oh.to(c.dev), out))}
     line = None
@@ -586,10 +607,11 @@ def run_clips(c: Ctx):
         line = {"metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": c.world, "steps": args.steps, "warmup": c.warm,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"cfg3: {w['desc']}", "clips": n_all, "clips_per_rank": n, "rows": rows, "frames_per_clip": T,
-                           "l2": "inputs larger than L2 (%.2f GB per rank per step)" % (n * L * 4 / 1e9),
+                "config": {"workload": f"{args.workload}: {w['desc']}", "clips": n_all, "clips_per_rank": n, "rows": rows, "frames_per_clip": T,
+                           "l2": ("inputs larger than L2 (%.2f GB per rank per step)" % (n * L * 4 / 1e9)) if n * L * 4 > (126 << 20)
+                                 else "one clip (0.9 MB) stays in L2 between steps: this line is a LATENCY figure, not a bandwidth one",
                            "parallelism": f"clips block-partitioned over {c.world} GPU(s); all-gather of the feature block inside the timed region"},
-                "roofline": roofline_block(c, alg, prof, args.steps, ms, "frame_warp_kernel<n_fft 512> (framing+window+rFFT+mel)",
+                "roofline": roofline_block(c, alg, prof, args.steps, ms, f"frame_warp_kernel<n_fft {w['fl']}> (framing+window+rFFT+mel)",
                                            None, {"finalize_ms_per_step": prof["finalize"][0] / args.steps}),
                 "clocks": clk, "gpu_launches": int(sum(prof[k][1] for k in prof))}
         if e2e:
