@@ -436,9 +436,10 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             const float tsq = lanes_sum<G>(sq2.x + sq2.y);
             const float tpk = lanes_max<G>(fmaxf(pk, pk2));
             if (j == 0 && valid) {
-                const float rms = sqrtf(tsq * (1.0f / (float)TL::NFFT));
+                const float rms = sqrt_approx(tsq * (1.0f / (float)TL::NFFT));     // MUFU.SQRT (1 ulp) instead of the IEEE sequence; bar: rel 1e-5
                 if (a.row_rms >= 0) orow[(long long)a.row_rms * a.T] = rms;
-                if (a.row_crest >= 0) orow[(long long)a.row_crest * a.T] = ((double)rms < kEps64) ? 0.0f : tpk / rms;
+                // eps(float64) = 2^-52 is a float too: the reference's `rms < eps` on the widened value is this float comparison
+                if (a.row_crest >= 0) orow[(long long)a.row_crest * a.T] = (rms < 2.220446049250313e-16f) ? 0.0f : __fdividef(tpk, rms);
                 if (a.row_peak >= 0) orow[(long long)a.row_peak * a.T] = tpk;
             }
             if (EXTRA) {
@@ -505,8 +506,14 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             const float tm = lanes_sum<G>(lsm);
             const float tkm = lanes_sum<G>(lskm);
             double centroid_hz = 0.0;
-            if ((double)tm >= kEps64) centroid_hz = a.bin_hz * ((double)tkm / (double)tm);
-            if (a.row_centroid >= 0 && j == 0 && valid) orow[(long long)a.row_centroid * a.T] = (float)centroid_hz;
+            if constexpr (EXTRA) {                                       // spectral_bandwidth needs the float64 centroid
+                if ((double)tm >= kEps64) centroid_hz = a.bin_hz * ((double)tkm / (double)tm);
+                if (a.row_centroid >= 0 && j == 0 && valid) orow[(long long)a.row_centroid * a.T] = (float)centroid_hz;
+            } else {
+                // the sums are FP32 already; one FP32 division (2^-23 relative against a 1e-5 parity bar) instead of a float64 one
+                const float c = (tm >= 2.220446049250313e-16f) ? (float)a.bin_hz * __fdividef(tkm, tm) : 0.0f;
+                if (a.row_centroid >= 0 && j == 0 && valid) orow[(long long)a.row_centroid * a.T] = c;
+            }
             if (a.row_rolloff >= 0) {
                 // first bin whose cumulative power reaches roll_percent * total (frequency_domain.py:334-346)
                 const double thr = a.roll_percent * total_p;

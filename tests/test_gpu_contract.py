@@ -278,3 +278,35 @@ def test_segment_fixed_length_invalid_params(ramp):
         segmentation.segment_fixed_length(y, sr, segment_length_sec=1.0, overlap_ratio=-0.1)
     with pytest.raises(ValueError):
         segmentation.segment_fixed_length(np.zeros((2, 10)), sr, 1.0)
+
+
+@pytest.mark.gpu
+def test_two_streams_share_one_engine_without_corrupting_the_workspace():
+    """the device entry points are asynchronous on the caller's stream but share the context's workspace (mel energies,
+    unit maxima).  Calls queued on two different torch streams must not overwrite each other's intermediates: the library orders
+    them with an event (`ws_done`).  Results must equal the single-stream results bit for bit."""
+    import torch
+    from sygnals_b200 import _ffi
+    from sygnals_b200.utils import synth
+    eng = _ffi.engine(0)
+    sr = 22050
+    feats = ["mfcc", "spectral_contrast", "rms_energy"]
+    p = _ffi.make_params(eng.lib, sr, feats, 2048, 512)
+    ys = [torch.from_numpy(synth.clip_batch(300, 3 * sr, sr, seed=40 + i, edges=False)).cuda() for i in range(2)]
+    units = eng.units_clips(300, 3 * sr)
+    rows, T = eng.rows(p), eng.frame_count(3 * sr, 2048, 512, True)
+    ref = []
+    for y in ys:
+        o = torch.empty((300, rows, T), dtype=torch.float32, device="cuda")
+        eng.features_dev(y.data_ptr(), units, p, o.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ref.append(o)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [torch.empty_like(ref[0]) for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(3):                                             # interleave the two streams several times
+        for i, st in enumerate(streams):
+            eng.features_dev(ys[i].data_ptr(), units, p, outs[i].data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert torch.equal(outs[i], ref[i])
