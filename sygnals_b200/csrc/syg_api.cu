@@ -537,14 +537,17 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
         f.cws = a.cws;
         f.unit_max = a.unit_max;
         f.out = out;
-        const size_t smem = (size_t)sygdev::kFinTT * sygdev::fin_pitch(f.n_mels) * sizeof(float);     // FP32 S_db tile
-        const long long n_tiles = (g.n_units * (long long)pl.T + sygdev::kFinTT - 1) / sygdev::kFinTT;
+        static int fin_tt = -1;                                       // SYGB200_FIN_TT=32|64 overrides the tile height (A/B)
+        if (fin_tt < 0) { const char* e = std::getenv("SYGB200_FIN_TT"); fin_tt = e ? std::atoi(e) : 0; }
+        const int tt = fin_tt == 32 || fin_tt == 64 ? fin_tt : ((f.row_mfcc >= 0 && f.n_mels <= 64) ? 64 : 32);
+        const size_t smem = (size_t)tt * sygdev::fin_pitch(f.n_mels) * sizeof(float);     // FP32 S_db tile
+        const long long n_tiles = (g.n_units * (long long)pl.T + tt - 1) / tt;
         static int fin_cap = -1;                                      // SYGB200_FIN_CTAS: CTAs per SM of the finalize grid (0 = one CTA per tile)
         if (fin_cap < 0) { const char* e = std::getenv("SYGB200_FIN_CTAS"); fin_cap = e ? std::atoi(e) : 0; }
         const long long cap = fin_cap > 0 ? (long long)ctx->sm_count * fin_cap : 0x7fffffffLL;
         const unsigned grid = (unsigned)std::min<long long>(n_tiles, cap);
         std::string err;
-        const int frc = syglaunch::finalize(f, grid, 1u, smem, st, err);
+        const int frc = syglaunch::finalize(f, tt, grid, 1u, smem, st, err);
         if (frc) return fail(frc, "%s", err.c_str());
     }
     return SYG_OK;
@@ -1251,7 +1254,7 @@ int syg_spectral_contrast_from_mag_f32(syg_ctx* ctx, const float* S_dev, int32_t
     f.cws = cws; f.unit_max = um; f.out = out_dev;
     if (T > 0x7fffffffLL) return fail(SYG_E_UNSUPPORTED, "too many frames");
     const long long n_tiles = (T + sygdev::kFinTT - 1) / sygdev::kFinTT;
-    rc = syglaunch::finalize(f, (unsigned)std::min<long long>(n_tiles, 0x7fffffffLL), 1u, 256, st, err);
+    rc = syglaunch::finalize(f, sygdev::kFinTT, (unsigned)std::min<long long>(n_tiles, 0x7fffffffLL), 1u, 256, st, err);
     return rc ? fail(rc, "%s", err.c_str()) : SYG_OK;
 }
 

@@ -43,7 +43,8 @@ SYG_DEVICE SYG_INLINE void mma_m8n8k4_f64(double& d0, double& d1, double av, dou
 // Persistent: the chunk's frames are one flat sequence cut into tiles of kFinTT consecutive frames (a tile may straddle units:
 // every slot carries its own unit, reference level and clamps), CTAs stride over the tiles.  Short units (T = 101 in the
 // speech-commands shape) no longer leave partial tiles or one tiny CTA per 32 frames.
-__global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeArgs a) {
+template <int kFinTT>
+__global__ void __launch_bounds__(kThreads) finalize_kernel_t(const syg::FinalizeArgs a) {
     SYG_DYN_SMEM(smem_raw);
     __shared__ long long s_out[kFinTT];         // offset of (unit, row 0, frame t) in `out`
     __shared__ float s_ref[kFinTT], s_floor[kFinTT], s_pfloor[kFinTT], s_vfloor[kFinTT];
@@ -125,12 +126,13 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const syg::FinalizeA
             // entry and ONE tile entry for 256 multiply-adds of the warp (the scalar version needed 1.5 loads per FMA and was
             // bound by the load/store unit: 3.5 ms per 10 h of audio).
             {
-                const int par = warp & 1, nt8 = (warp >> 1) * 8;       // kThreads / 32 = 8 warps: 2 parities x 4 n-tiles of 8 frames
+                const int par = warp & 1;                               // kThreads / 32 = 8 warps: 2 parities x 4 n-tiles of 8 frames (per 32 frames)
                 const int g = lane >> 2, q = lane & 3;
                 const int n_par = par ? a.n_mfcc / 2 : (a.n_mfcc + 1) / 2;
-                const float* const xrow = xs + (nt8 + g) * P;            // this lane's frame (B column)
                 const double sgn = par ? -1.0 : 1.0;
+                for (int nt8 = (warp >> 1) * 8; nt8 < kFinTT; nt8 += 32)
                 for (int m0 = 0; m0 < n_par; m0 += 8) {
+                    const float* const xrow = xs + (nt8 + g) * P;        // this lane's frame (B column)
                     const int c_a = par + 2 * (m0 + g);                 // coefficient of this lane's A row
                     const bool a_ok = c_a < a.n_mfcc;
                     const double* const drow = a.dct + (long long)(a_ok ? c_a : 0) * N + q;

@@ -14,7 +14,7 @@ int stft_ring(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st,
 // n_fft 4096 / 8192, real-valued output: 1024-point sub-FFTs per warp + recombination (syg_stft_big.cuh)
 int stft_big(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 int frame_warp_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
-int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err);
+int finalize(const syg::FinalizeArgs& a, int tt, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err);
 int aggregate(const float* feats, long long n_seg, int n_rows, long long row_stride, const long long* seg_off, const int* seg_len,
               int fixed_len, const int* agg_host, double* out, int sm_count, cudaStream_t st, std::string& err);
 int time_extra(const syg::FrameArgs& a, int frame_length, int entropy_bins, int sm_count, cudaStream_t st, std::string& err);

@@ -68,15 +68,22 @@ int frame_block(int n_fft, int mode, const syg::FrameArgs& a, int sm_count, cuda
     return -5;
 }
 
-int finalize(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err) {
+template <int TT>
+static int finalize_t(const syg::FinalizeArgs& a, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err) {
+    auto kfn = sygdev::finalize_kernel_t<TT>;
     if (smem > 48 * 1024) {                         // the S_db tile exceeds the default 48 KB for wide mel banks
         static KernelCache kc;
         int nb = 0;
-        if (int rc = prepare_kernel(sygdev::finalize_kernel, sygdev::kThreads, smem, kc, &nb, err)) return rc;
+        if (int rc = prepare_kernel(kfn, sygdev::kThreads, smem, kc, &nb, err)) return rc;
     }
-    SYG_LAUNCH(sygdev::finalize_kernel, dim3(grid_x, grid_y), dim3(sygdev::kThreads), smem, st, a);
+    SYG_LAUNCH(kfn, dim3(grid_x, grid_y), dim3(sygdev::kThreads), smem, st, a);
     LCK(cudaGetLastError());
     return 0;
+}
+
+// tt = frames per CTA tile: 32 (default) or 64 (narrow mel banks: the CTA is latency bound, twice the frames amortise it)
+int finalize(const syg::FinalizeArgs& a, int tt, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err) {
+    return tt == 64 ? finalize_t<64>(a, grid_x, grid_y, smem, st, err) : finalize_t<32>(a, grid_x, grid_y, smem, st, err);
 }
 
 }  // namespace syglaunch
