@@ -88,7 +88,8 @@ typedef struct {
 /* extract_features(y, sr, features, frame_length, hop_length, center, window, feature_params)  manager.py:78-88 */
 typedef struct {
     int32_t sr;
-    int32_t frame_length; /* = n_fft = win_length (manager.py:184-187); power of two, 32..8192 */
+    int32_t frame_length; /* = n_fft = win_length (manager.py:184-187); a power of two in 32..8192, or any
+                           * length >= 8 with prime factors <= 13 that fits in shared memory (mixed-radix kernels) */
     int32_t hop_length;
     int32_t center;       /* 1: zero-pad frame_length/2 both sides */
     int32_t window;       /* SYG_WINDOW_* */
@@ -180,7 +181,8 @@ int syg_stft_host_f32(syg_ctx* ctx, const float* y_host, const syg_units* units,
                       void* out_host);
 
 /* compute_psd_welch() per unit: psd [n_units][1 + nfft/2]; stats (optional) [n_units][3] = rms, crest, peak of
- * the unit.  noverlap < 0: nperseg/2; nfft <= 0: nperseg (power of two, 32..8192). */
+ * the unit.  noverlap < 0: nperseg/2; nfft <= 0: nperseg (a power of two in 32..8192, or
+ * any length >= 8 with prime factors <= 13 up to 28 800: the mixed-radix kernels). */
 int syg_psd_welch_f32(syg_ctx* ctx, const float* y_dev, const syg_units* units, double fs, int32_t window,
                       int32_t nperseg, int32_t noverlap, int32_t nfft, int32_t detrend_constant, int32_t scaling,
                       float* psd_dev, float* stats_dev, void* stream);

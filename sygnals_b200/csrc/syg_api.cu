@@ -222,6 +222,44 @@ int get_half_split_twiddles(syg_ctx* ctx, int n_fft, const float2** out) {
     return upload_table(ctx, kh, h, out);
 }
 
+// ---- transform lengths outside the power-of-two kernels (syg_mixed.cuh): smooth lengths (prime factors <= 13) whose buffers fit
+// in one SM's shared memory; powers of two above 8192 take the same route
+constexpr size_t kMaxDynSmem = 227 * 1024;
+bool native_pow2(long long n) { return is_pow2(n) && n >= 32 && n <= 8192; }
+
+int mixed_plan_of(int n, bool features, syg::MixedPlan& mp, const char* what) {
+    std::memset(&mp, 0, sizeof(mp));
+    if (n < 8) return fail(SYG_E_UNSUPPORTED, "%s=%d: transform lengths below 8 are not supported", what, n);
+    mp.n = n;
+    mp.packed = (n % 2 == 0) ? 1 : 0;
+    mp.L = mp.packed ? n / 2 : n;
+    mp.B = n / 2 + 1;
+    std::vector<int> r;
+    if (!sygplan::factorize_smooth(mp.L, r) || r.size() > 24)
+        return fail(SYG_E_UNSUPPORTED, "%s=%d: only lengths whose prime factors are at most 13 are supported", what, n);
+    if (sygdev::mixed_layout(mp.L, mp.B, features).bytes > kMaxDynSmem)
+        return fail(SYG_E_UNSUPPORTED, "%s=%d: the transform does not fit in shared memory", what, n);
+    mp.npass = (int)r.size();
+    for (int i = 0; i < mp.npass; ++i) mp.radix[i] = r[i];
+    return SYG_OK;
+}
+
+// tw = exp(-2 pi i p / L), p < L, for the mixed-radix passes; tws = real-split twiddles (packed transforms only)
+int get_mixed_tables(syg_ctx* ctx, int n, const float2** tw, const float2** tws) {
+    if (n % 2 == 0) return get_fft_tables(ctx, n, tw, tws);
+    *tws = nullptr;
+    std::string k = keyf("twodd:%d", n);
+    std::vector<float2> a;
+    if (!ctx->tables.count(k)) {
+        a.resize(n);
+        for (int p = 0; p < n; ++p) {
+            const double ang = -2.0 * sygplan::kPi * (double)p / (double)n;
+            a[p] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+    }
+    return upload_table(ctx, k, a, tw);
+}
+
 int get_window(syg_ctx* ctx, int window, int win_length, int n_fft, bool centred, const float** out) {
     std::string key = keyf("win:%d:%d:%d:%d", window, win_length, n_fft, (int)centred);
     std::vector<float> w;
@@ -249,6 +287,11 @@ int launch_features(int n_fft, const syg::FrameArgs& a_in, int sm_count, cudaStr
     if (variant < 0) { const char* e = std::getenv("SYGB200_VARIANT"); variant = e ? std::atoi(e) : 0; }
     syg::FrameArgs a = a_in;
     a.variant = variant;
+    if (!native_pow2(n_fft)) {
+        syg::MixedPlan mp;
+        if (int rc = mixed_plan_of(n_fft, true, mp, "frame_length")) return rc;
+        return launch_rc(syglaunch::frame_mixed(sygdev::MODE_FEATURES, a, mp, sm_count, st, err), err);
+    }
     if (n_fft > 2048) return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_FEATURES, a, sm_count, st, err), err);
     constexpr unsigned extra = syg::FB_BANDWIDTH | syg::FB_FLATNESS | syg::FB_DOMINANT | syg::FB_MEAN_AMP | syg::FB_STD_AMP;
     return launch_rc(syglaunch::frame_warp(n_fft, (a.mask & extra) != 0, a, sm_count, st, err), err);
@@ -259,12 +302,18 @@ int warp_fw(int n_fft) {
     switch (ilog2i(n_fft / 2)) { case 4: return 8; case 5: return 8; case 6: return 4; case 7: return 4; case 8: return 2; case 9: return 2; default: return 1; }
 }
 
-int g_last_stft_path = 0;   // 1 ring (TMA-staged), 2 warp kernel (register-staged), 3 CTA-cooperative kernels, 4 sub-FFT kernel (n_fft 4096 / 8192): last STFT launch
+int g_last_stft_path = 0;   // 5 mixed-radix kernel (lengths that are not powers of two), 1 ring (TMA-staged), 2 warp kernel (register-staged), 3 CTA-cooperative kernels, 4 sub-FFT kernel (n_fft 4096 / 8192): last STFT launch
 
 int launch_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
     std::string err;
     static int env = -1;                                                // SYGB200_STFT_BLOCK=1: the CTA-cooperative kernel for every n_fft
     if (env < 0) { const char* e = std::getenv("SYGB200_STFT_BLOCK"); env = e ? std::atoi(e) : 0; }
+    if (!native_pow2(n_fft)) {
+        syg::MixedPlan mp;
+        if (int rc = mixed_plan_of(n_fft, false, mp, "n_fft")) return rc;
+        g_last_stft_path = 5;
+        return launch_rc(syglaunch::frame_mixed(sygdev::MODE_STFT, a, mp, sm_count, st, err), err);
+    }
     if (n_fft >= 4096 && !env && a.out_kind != 0) {
         g_last_stft_path = 4;
         return launch_rc(syglaunch::stft_big(n_fft, a, sm_count, st, err), err);
@@ -281,6 +330,11 @@ int launch_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t s
 
 int launch_welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st) {
     std::string err;
+    if (!native_pow2(nfft)) {
+        syg::MixedPlan mp;
+        if (int rc = mixed_plan_of(nfft, false, mp, "nfft")) return rc;
+        return launch_rc(syglaunch::welch_mixed(a, mp, sm_count, st, err), err);
+    }
     return launch_rc(syglaunch::welch(nfft, a, sm_count, st, err), err);
 }
 
@@ -343,8 +397,11 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
     if (!p) return fail(SYG_E_BADARG, "params is NULL");
     if (p->sr <= 0) return fail(SYG_E_BADARG, "sr must be positive");
     const int fl = p->frame_length;
-    if (!is_pow2(fl) || fl < 32 || fl > 8192)
-        return fail(SYG_E_UNSUPPORTED, "frame_length=%d: only powers of two in [32, 8192] are supported", fl);
+    const bool mixed = !native_pow2(fl);
+    if (mixed) {
+        syg::MixedPlan mp;
+        if (int mrc = mixed_plan_of(fl, true, mp, "frame_length")) return mrc;
+    }
     if (p->hop_length < 1) return fail(SYG_E_BADARG, "hop_length must be >= 1");
     int32_t rows = 0;
     int rc = rows_of(p, &rows);
@@ -392,9 +449,9 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
     a.roll_percent = p->roll_percent;
     rc = get_window(ctx, p->window, fl, fl, true, &a.window);
     if (rc) return rc;
-    rc = get_fft_tables(ctx, fl, &a.tw, &a.tws);
+    rc = mixed ? get_mixed_tables(ctx, fl, &a.tw, &a.tws) : get_fft_tables(ctx, fl, &a.tw, &a.tws);
     if (rc) return rc;
-    if ((rc = get_half_split_twiddles(ctx, fl, &a.twsh))) return rc;
+    if (!mixed && (rc = get_half_split_twiddles(ctx, fl, &a.twsh))) return rc;
     size_t ws = 0;
     if (mask & syg::FB_MFCC) {
         if (p->n_mels < 1 || p->n_mels > 256) return fail(SYG_E_UNSUPPORTED, "n_mels=%d: supported range is [1, 256]", p->n_mels);
@@ -412,6 +469,7 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
         if ((rc = upload_table(ctx, key + ":l", mt.len, &a.mel_len))) return rc;
         if ((rc = upload_table(ctx, key + ":o", mt.off, &a.mel_off))) return rc;
         if ((rc = upload_table(ctx, key + ":w", mt.w, &a.mel_w))) return rc;
+        if (!mixed) {
         sygplan::MelSlots ms;
         if (!ctx->tables.count(key + ":pw")) sygplan::build_mel_slots(mt, ms, fl / 2 + 1, fl <= 2048 ? 32 / warp_fw(fl) : 32);
         std::vector<int4> slots(ms.desc.size() / 4);
@@ -461,6 +519,8 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
                 }
             }
         }
+        }                                                            // !mixed: the mixed-radix kernel reads the compact tap table only
+        a.n_mels = p->n_mels;
         a.mel_power_is_2 = (p->power == 2.0);
         a.mel_half_power = (float)(0.5 * p->power);
         std::string dk = keyf("dct64:%d:%d:%d:%d:%.9g", p->n_mfcc, p->n_mels, p->dct_type, p->dct_ortho, (double)p->lifter);
@@ -707,8 +767,11 @@ syg::UnitGeom chunk_geom(const syg_units& cu, long long shift) {
 
 int stft_setup(syg_ctx* ctx, const syg_units* u, int n_fft, int hop, int win_length, int window, int center, int pad_mode,
                int out_kind, syg::FrameArgs& a) {
-    if (!is_pow2(n_fft) || n_fft < 32 || n_fft > 8192)
-        return fail(SYG_E_UNSUPPORTED, "n_fft=%d: only powers of two in [32, 8192] are supported", n_fft);
+    const bool mixed = !native_pow2(n_fft);
+    if (mixed) {
+        syg::MixedPlan mp;
+        if (int mrc = mixed_plan_of(n_fft, false, mp, "n_fft")) return mrc;
+    }
     if (hop < 1) return fail(SYG_E_BADARG, "hop_length must be >= 1");
     if (win_length < 1 || win_length > n_fft) return fail(SYG_E_BADARG, "win_length must be in [1, n_fft]");
     if (pad_mode != SYG_PAD_CONSTANT && pad_mode != SYG_PAD_REFLECT) return fail(SYG_E_UNSUPPORTED, "unsupported pad_mode %d", pad_mode);
@@ -725,6 +788,7 @@ int stft_setup(syg_ctx* ctx, const syg_units* u, int n_fft, int hop, int win_len
     a.out_kind = out_kind;
     int rc = get_window(ctx, window, win_length, n_fft, true, &a.window);
     if (rc) return rc;
+    if (mixed) return get_mixed_tables(ctx, n_fft, &a.tw, &a.tws);
     if (n_fft >= 4096) {                                                // stft_big_kernel: 1024-point sub-transforms + recombination
         const float2* unused = nullptr;
         if ((rc = get_fft_tables(ctx, 2048, &a.tw1k, &unused))) return rc;
@@ -746,8 +810,11 @@ int welch_setup(syg_ctx* ctx, const syg_units* u, double fs, int window, int npe
     if (noverlap < 0) noverlap = nperseg / 2;
     if (noverlap >= nperseg) return fail(SYG_E_BADARG, "noverlap must be less than nperseg.");
     if (nfft < nperseg) return fail(SYG_E_BADARG, "nfft must be greater than or equal to nperseg.");
-    if (!is_pow2(nfft) || nfft < 32 || nfft > 8192)
-        return fail(SYG_E_UNSUPPORTED, "nfft=%d: only powers of two in [32, 8192] are supported", nfft);
+    const bool mixed = !native_pow2(nfft);
+    if (mixed) {
+        syg::MixedPlan mp;
+        if (int mrc = mixed_plan_of(nfft, false, mp, "nfft")) return mrc;
+    }
     if (u->unit_len < nperseg) return fail(SYG_E_SHAPE, "unit_len=%lld shorter than nperseg=%d", (long long)u->unit_len, nperseg);
     if (scaling != SYG_SCALING_DENSITY && scaling != SYG_SCALING_SPECTRUM) return fail(SYG_E_BADARG, "unknown scaling %d", scaling);
     if (window < 0 || window > 3) return fail(SYG_E_UNSUPPORTED, "unsupported window id %d", window);
@@ -764,7 +831,7 @@ int welch_setup(syg_ctx* ctx, const syg_units* u, double fs, int window, int npe
     a.onesided_double = 1;
     int rc = get_window(ctx, window, nperseg, nfft, false, &a.window);
     if (rc) return rc;
-    return get_fft_tables(ctx, nfft, &a.tw, &a.tws);
+    return mixed ? get_mixed_tables(ctx, nfft, &a.tw, &a.tws) : get_fft_tables(ctx, nfft, &a.tw, &a.tws);
 }
 
 }  // namespace

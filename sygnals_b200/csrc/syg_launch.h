@@ -24,5 +24,8 @@ int dct_matrix(const double* S, const double* D, long long n_units, int N, long 
                std::string& err);
 int contrast_spectrum(const float* S, int B, long long T, int nb, const int* lo, const int* cnt, const int* nq, float* cws, unsigned* unit_max,
                       int sm_count, cudaStream_t st, std::string& err);
+// transform lengths that are not powers of two (syg_mixed.cuh): mode = MODE_FEATURES / MODE_STFT
+int frame_mixed(int mode, const syg::FrameArgs& a, const syg::MixedPlan& mp, int sm_count, cudaStream_t st, std::string& err);
+int welch_mixed(const syg::WelchArgs& a, const syg::MixedPlan& mp, int sm_count, cudaStream_t st, std::string& err);
 int welch(int nfft, const syg::WelchArgs& a, int sm_count, cudaStream_t st, std::string& err);
 }  // namespace syglaunch

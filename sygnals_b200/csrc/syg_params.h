@@ -14,6 +14,27 @@ constexpr int kFinTT = 32;                  // frames per finalize CTA
 __host__ __device__
 #endif
 inline int fin_pitch(int N) { int p = (N + 3) / 4 * 4; while ((p & 7) != 4) p += 4; return p; }
+
+// shared-memory layout (float words) of the mixed-radix kernels for L complex points and B bins
+struct MixedLayout {
+    int off_a, off_b, off_pw, off_cand, off_smax, off_dsc_f, total_f;
+    size_t bytes;
+};
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline MixedLayout mixed_layout(int L, int B, bool features) {
+    MixedLayout m;
+    m.off_a = 0;
+    m.off_b = 2 * L;
+    m.off_pw = 4 * L;
+    m.off_cand = m.off_pw + (features ? (B + (B >> 5) + 1) : 0);
+    m.off_smax = m.off_cand + (features ? (kThreads / 32) * 32 : 0);
+    m.off_dsc_f = ((m.off_smax + 4 + 1) / 2) * 2;
+    m.total_f = m.off_dsc_f + 2 * (kThreads / 32 + kThreads);
+    m.bytes = (size_t)m.total_f * 4;
+    return m;
+}
 }  // namespace sygdev
 
 namespace syg {
@@ -88,6 +109,13 @@ struct FrameArgs {
     // ---- stft
     int out_kind;               // 0 complex64, 1 magnitude, 2 power
     void* stft_out;             // [n_units][B][T]
+};
+
+// run-time plan of the mixed-radix kernels (syg_mixed.cuh): n real samples per transform, L complex points in shared memory
+// (n/2 packed when n is even, n otherwise), B = n/2 + 1 one-sided bins, the radices of the passes in order
+struct MixedPlan {
+    int n, L, B, packed, npass;
+    int radix[24];
 };
 
 struct FinalizeArgs {

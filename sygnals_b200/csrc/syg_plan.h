@@ -53,6 +53,17 @@ inline double window_value_d(int window, int win_length, int n) {
     return w;
 }
 
+// Radices of the mixed-radix kernels for an L-point transform: fours first, then 2 / 3 / 5 / 7 / 11 / 13.  false if L has a larger
+// prime factor (those lengths stay unsupported).
+inline bool factorize_smooth(int L, std::vector<int>& radix) {
+    radix.clear();
+    if (L < 1) return false;
+    while (L % 4 == 0) { radix.push_back(4); L /= 4; }
+    for (int p : {2, 3, 5, 7, 11, 13})
+        while (L % p == 0) { radix.push_back(p); L /= p; }
+    return L == 1;
+}
+
 // numpy.fft.rfftfreq(n_fft, 1/sr) step, with numpy's operation order
 inline double bin_hz(double sr, int n_fft) {
     const double d = 1.0 / sr;

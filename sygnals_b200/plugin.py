@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import importlib
 import logging
+import operator
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
 from . import __version__, _ffi
@@ -58,8 +59,31 @@ _REBIND_TARGETS: List[Tuple[str, str, Tuple[str, ...]]] = [
 ]
 
 
-def _pow2_in_range(n: int, lo: int = 32, hi: int = 8192) -> bool:
-    return isinstance(n, int) and lo <= n <= hi and (n & (n - 1)) == 0
+def _length_ok(n, features: bool = False) -> bool:
+    """Transform lengths the engine serves: powers of two in [32, 8192] on the register-FFT kernels; every other length >= 8 whose
+    prime factors are at most 13 and whose buffers fit in one SM's shared memory on the mixed-radix kernels (syg_mixed.cuh;
+    mirrors ``mixed_plan_of`` in csrc/syg_api.cu -- the library re-checks and the plugin falls back on NotImplementedError)."""
+    try:
+        n = operator.index(n)
+    except TypeError:
+        return False
+    if n < 8:
+        return False
+    if 32 <= n <= 8192 and (n & (n - 1)) == 0:
+        return True
+    L = n // 2 if n % 2 == 0 else n
+    m = L
+    for p in (2, 3, 5, 7, 11, 13):
+        while m % p == 0:
+            m //= p
+    if m != 1:
+        return False
+    B = n // 2 + 1
+    words = 4 * L + ((B + (B >> 5) + 1 + 256) if features else 0) + 6 + 2 * (8 + 256)
+    return words * 4 <= 227 * 1024
+
+
+_LENGTH_RULE = "a power of two in [32, 8192] or a length >= 8 with prime factors <= 13 that fits in shared memory"
 
 
 class SygnalsB200Plugin(SygnalsPluginBase):
@@ -134,8 +158,8 @@ class SygnalsB200Plugin(SygnalsPluginBase):
                       output_format=output_format)
             reason = None
             names = sorted(m._ALL_KNOWN_FEATURES) if features == ["all"] else list(features)
-            if not _pow2_in_range(frame_length):
-                reason = f"frame_length={frame_length} is not a power of two in [32, 8192]"
+            if not _length_ok(frame_length, features=True):
+                reason = f"frame_length={frame_length} is not {_LENGTH_RULE}"
             elif not isinstance(window, str) or window.lower() not in _ffi.WINDOW_IDS:
                 reason = f"window={window!r} is not built into the engine"
             if reason is not None:
@@ -183,8 +207,8 @@ class SygnalsB200Plugin(SygnalsPluginBase):
 
         def compute_stft(y, n_fft=2048, hop_length=None, win_length=None, window="hann", center=True, pad_mode="constant"):
             reason = None
-            if not _pow2_in_range(n_fft):
-                reason = f"n_fft={n_fft} is not a power of two in [32, 8192]"
+            if not _length_ok(n_fft):
+                reason = f"n_fft={n_fft} is not {_LENGTH_RULE}"
             elif not isinstance(window, str) or window.lower() not in _ffi.WINDOW_IDS:
                 reason = f"window={window!r} is not built into the engine"
             elif pad_mode not in _ffi.PAD_IDS:
@@ -216,8 +240,8 @@ class SygnalsB200Plugin(SygnalsPluginBase):
             if which == "compute_psd_welch" and kw.get("nfft") is None:
                 nfft = min(int(nfft), n) if n else nfft                 # scipy clamps nperseg to the signal length
             reason = None
-            if not _pow2_in_range(int(nfft)):
-                reason = f"nfft={nfft} is not a power of two in [32, 8192]"
+            if not _length_ok(int(nfft)):
+                reason = f"nfft={nfft} is not {_LENGTH_RULE}"
             elif not isinstance(window, str) or window.lower() not in _ffi.WINDOW_IDS:
                 reason = f"window={window!r} is not built into the engine"
             elif kw.get("detrend", "constant") not in ("constant", True, False):
@@ -248,8 +272,8 @@ class SygnalsB200Plugin(SygnalsPluginBase):
         def feature(y=None, *args, **kw):
             fl = args[0] if args else kw.get("frame_length", 2048)
             reason = None
-            if not _pow2_in_range(fl):
-                reason = f"frame_length={fl} is not a power of two in [32, 8192]"
+            if not _length_ok(fl, features=True):
+                reason = f"frame_length={fl} is not {_LENGTH_RULE}"
             elif kw.get("S") is not None:
                 reason = "spectrogram input has no CUDA kernel"
             elif kw.get("pad_mode", "constant") != "constant":

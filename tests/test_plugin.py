@@ -63,19 +63,19 @@ def test_reference_loader_accepts_the_plugin_and_rebinding_round_trips():
         assert dsp.compute_stft is not orig[2] and sc.segment_fixed_length is not orig[3]
         # unsupported features stay on the reference path (routed to the ORIGINAL function, bit-identical result)
         y = np.sin(np.arange(4000) * 0.05)
-        a = fc.extract_features(y, 22050, ["zero_crossing_rate"], frame_length=500, hop_length=125, output_format="dict_of_arrays")
-        b = orig[0](y, 22050, ["zero_crossing_rate"], frame_length=500, hop_length=125, output_format="dict_of_arrays")
+        a = fc.extract_features(y, 22050, ["zero_crossing_rate"], frame_length=502, hop_length=125, output_format="dict_of_arrays")
+        b = orig[0](y, 22050, ["zero_crossing_rate"], frame_length=502, hop_length=125, output_format="dict_of_arrays")
         np.testing.assert_array_equal(a["zero_crossing_rate"], b["zero_crossing_rate"])
-        a = dsp.compute_stft(y, n_fft=300)                      # non power of two -> reference
-        np.testing.assert_array_equal(a, orig[2](y, n_fft=300))
+        a = dsp.compute_stft(y, n_fft=298)                      # 2 * 149: a prime factor above 13 -> reference
+        np.testing.assert_array_equal(a, orig[2](y, n_fft=298))
         # array-level audio features: rebound, unsupported geometry routed to the ORIGINAL (bit-identical)
         import sygnals.core.audio.features as af
         assert getattr(af.rms_energy, "__wrapped_reference__", None) is not None
-        r_a = af.rms_energy(y=y, frame_length=500, hop_length=125)
-        r_b = af.rms_energy.__wrapped_reference__(y=y, frame_length=500, hop_length=125)
+        r_a = af.rms_energy(y=y, frame_length=502, hop_length=125)
+        r_b = af.rms_energy.__wrapped_reference__(y=y, frame_length=502, hop_length=125)
         np.testing.assert_array_equal(r_a, r_b)
-        z_a = af.zero_crossing_rate(y, frame_length=500, hop_length=125)
-        np.testing.assert_array_equal(z_a, af.zero_crossing_rate.__wrapped_reference__(y, frame_length=500, hop_length=125))
+        z_a = af.zero_crossing_rate(y, frame_length=502, hop_length=125)
+        np.testing.assert_array_equal(z_a, af.zero_crossing_rate.__wrapped_reference__(y, frame_length=502, hop_length=125))
         # error contract unchanged (manager.py:141-143)
         with pytest.raises(ValueError, match="Unknown feature"):
             fc.extract_features(y, 22050, ["nope"])
@@ -96,8 +96,8 @@ def test_strict_mode_refuses_unsupported_instead_of_falling_back():
     fn = p.make_extract_features(original=lambda *a, **k: pytest.fail("must not reach the reference"))
     with pytest.raises(NotImplementedError, match="no CUDA kernel"):
         fn(np.zeros(4096), 22050, ["jitter"])
-    with pytest.raises(NotImplementedError, match="power of two"):
-        fn(np.zeros(4096), 22050, ["mfcc"], frame_length=1000)
+    with pytest.raises(NotImplementedError, match="prime factors"):
+        fn(np.zeros(4096), 22050, ["mfcc"], frame_length=1006)     # 2 * 503
 
 
 @pytest.mark.gpu
@@ -183,7 +183,7 @@ def test_psd_wrappers_accept_positional_arguments():
         return "ref"
 
     fn = p._make_psd("compute_psd_welch", ref)
-    assert fn(np.zeros(3000), 1000.0, "hann", 1000, 500) == "ref"        # nperseg 1000 is not a power of two -> reference, same arguments
-    assert seen == {"nperseg": 1000, "noverlap": 500}
+    assert fn(np.zeros(3000), 1000.0, "hann", 1006, 500) == "ref"        # nperseg 1006 = 2 * 503: no kernel -> reference, same arguments
+    assert seen == {"nperseg": 1006, "noverlap": 500}
     with pytest.raises(TypeError):
-        fn(np.zeros(3000), 1000.0, "hann", 1000, nperseg=512)
+        fn(np.zeros(3000), 1000.0, "hann", 1006, nperseg=512)
