@@ -1,7 +1,7 @@
 // sygnals_b200/csrc/syg_mixed.cuh
 //
 // Transforms whose length is NOT a power of two (frame_length 400 / 1000 / 1200, the 25 600-sample second of BASELINE config 5,
-// odd lengths): one CTA per frame, a Stockham autosort FFT in shared memory with run-time radices 4 / 2 / 3 / 5 / 7 / 11 / 13.
+// odd lengths): one CTA (64 / 128 / 256 threads by length) per frame, a Stockham autosort FFT in shared memory with run-time radices 4 / 2 / 3 / 5 / 7 / 11 / 13.
 //
 //   frame_mixed_kernel<MODE>   MODE_FEATURES: the feature rows of frame_kernel (syg_kernels.cuh) for any smooth frame_length
 //                              MODE_STFT:     complex / magnitude / power spectrogram (dsp.py:167-229)
@@ -86,11 +86,11 @@ SYG_DEVICE SYG_INLINE void dft_small(float2* v, const float2* __restrict__ tw, i
     }
 }
 
-template <int R>
+template <int R, int NT>
 SYG_DEVICE SYG_INLINE void mixed_pass(const float2* src, float2* dst, int L, int Ns, const float2* __restrict__ tw, int tid) {
     const int LR = L / R;
     const int tmul = L / (Ns * R);
-    for (int j = tid; j < LR; j += kThreads) {
+    for (int j = tid; j < LR; j += NT) {
         const int k = j % Ns;
         float2 v[R];
         SYG_UNROLL
@@ -111,6 +111,7 @@ SYG_DEVICE SYG_INLINE void mixed_pass(const float2* src, float2* dst, int L, int
 }
 
 // all passes of the plan; returns the buffer that holds the spectrum (natural order).  Ends with a CTA barrier.
+template <int NT>
 SYG_DEVICE SYG_INLINE float2* mixed_fft(float2* a, float2* b, const syg::MixedPlan& mp, const float2* __restrict__ tw, int tid) {
     float2* src = a;
     float2* dst = b;
@@ -118,13 +119,13 @@ SYG_DEVICE SYG_INLINE float2* mixed_fft(float2* a, float2* b, const syg::MixedPl
     for (int p = 0; p < mp.npass; ++p) {
         const int R = mp.radix[p];
         switch (R) {
-            case 2: mixed_pass<2>(src, dst, mp.L, Ns, tw, tid); break;
-            case 3: mixed_pass<3>(src, dst, mp.L, Ns, tw, tid); break;
-            case 4: mixed_pass<4>(src, dst, mp.L, Ns, tw, tid); break;
-            case 5: mixed_pass<5>(src, dst, mp.L, Ns, tw, tid); break;
-            case 7: mixed_pass<7>(src, dst, mp.L, Ns, tw, tid); break;
-            case 11: mixed_pass<11>(src, dst, mp.L, Ns, tw, tid); break;
-            default: mixed_pass<13>(src, dst, mp.L, Ns, tw, tid); break;
+            case 2: mixed_pass<2, NT>(src, dst, mp.L, Ns, tw, tid); break;
+            case 3: mixed_pass<3, NT>(src, dst, mp.L, Ns, tw, tid); break;
+            case 4: mixed_pass<4, NT>(src, dst, mp.L, Ns, tw, tid); break;
+            case 5: mixed_pass<5, NT>(src, dst, mp.L, Ns, tw, tid); break;
+            case 7: mixed_pass<7, NT>(src, dst, mp.L, Ns, tw, tid); break;
+            case 11: mixed_pass<11, NT>(src, dst, mp.L, Ns, tw, tid); break;
+            default: mixed_pass<13, NT>(src, dst, mp.L, Ns, tw, tid); break;
         }
         __syncthreads();
         float2* t = src; src = dst; dst = t;
@@ -135,11 +136,11 @@ SYG_DEVICE SYG_INLINE float2* mixed_fft(float2* a, float2* b, const syg::MixedPl
 
 // Visits every bin of the one-sided spectrum once: fn(k, re, im).  packed: real split of the L-point packed transform (bins
 // 0..L); otherwise the first B bins of the n-point transform.
-template <class Fn>
+template <int NT, class Fn>
 SYG_DEVICE SYG_INLINE void mixed_bins(const float2* z, const syg::MixedPlan& mp, const float2* __restrict__ tws, int tid, Fn fn) {
     const int L = mp.L;
     if (mp.packed) {
-        for (int k = tid; k <= L / 2; k += kThreads) {
+        for (int k = tid; k <= L / 2; k += NT) {
             const int km = k ? L - k : 0;
             const float2 zk = SLD(&z[k]), zm = SLD(&z[km]);
             const float2 w = __ldg(&tws[k]);
@@ -149,18 +150,18 @@ SYG_DEVICE SYG_INLINE void mixed_bins(const float2* z, const syg::MixedPlan& mp,
             if (L - k != k) fn(L - k, xmr, xmi);
         }
     } else {
-        for (int k = tid; k < mp.B; k += kThreads) {
+        for (int k = tid; k < mp.B; k += NT) {
             const float2 v = SLD(&z[k]);
             fn(k, v.x, v.y);
         }
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameArgs a, const syg::MixedPlan mp) {
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT) frame_mixed_kernel(const syg::FrameArgs a, const syg::MixedPlan mp) {
     SYG_DYN_SMEM(smem_raw);
     const int L = mp.L, B = mp.B, N = mp.n;
-    const MixedLayout lay = mixed_layout(L, B, MODE == MODE_FEATURES);
+    const MixedLayout lay = mixed_layout(L, B, MODE == MODE_FEATURES, NT);
     float* const smf = reinterpret_cast<float*>(smem_raw);
     float2* const bufa = reinterpret_cast<float2*>(smf + lay.off_a);
     float2* const bufb = reinterpret_cast<float2*>(smf + lay.off_b);
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
     float* const cand = smf + lay.off_cand;
     unsigned* const smax = reinterpret_cast<unsigned*>(smf + lay.off_smax);
     double* const dsc = reinterpret_cast<double*>(smf + lay.off_dsc_f);
-    double* const dinc = dsc + kThreads / 32;
+    double* const dinc = dsc + NT / 32;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
 
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
         double s_sq = 0.0, s_sum = 0.0, s_abs = 0.0;
         float pk = 0.0f;
         if (mp.packed) {
-            for (int c = tid; c < L; c += kThreads) {
+            for (int c = tid; c < L; c += NT) {
                 const float2 v = load_pair(a.y, ur, p0 + 2 * c, a.pad_mode);
                 const float2 w = __ldg(reinterpret_cast<const float2*>(a.window) + c);
                 if (MODE == MODE_FEATURES) {
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
                 SST(&bufa[c], make_float2(v.x * w.x, v.y * w.y));
             }
         } else {
-            for (int c = tid; c < L; c += kThreads) {
+            for (int c = tid; c < L; c += NT) {
                 const float v = load_one(a.y, ur, p0 + c, a.pad_mode);
                 const float w = __ldg(a.window + c);
                 if (MODE == MODE_FEATURES) {
@@ -208,17 +209,17 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
             }
         }
         __syncthreads();
-        const float2* const z = mixed_fft(bufa, bufb, mp, a.tw, tid);
+        const float2* const z = mixed_fft<NT>(bufa, bufb, mp, a.tw, tid);
 
         if (MODE == MODE_STFT) {
             const long long ob = ((long long)u * B) * a.T + t;
             if (a.out_kind == 0) {
                 float2* o = reinterpret_cast<float2*>(a.stft_out);
-                mixed_bins(z, mp, a.tws, tid, [&](int k, float re, float im) { o[ob + (long long)k * a.T] = make_float2(re, im); });
+                mixed_bins<NT>(z, mp, a.tws, tid, [&](int k, float re, float im) { o[ob + (long long)k * a.T] = make_float2(re, im); });
             } else {
                 float* o = reinterpret_cast<float*>(a.stft_out);
                 const bool mag = a.out_kind == 1;
-                mixed_bins(z, mp, a.tws, tid, [&](int k, float re, float im) {
+                mixed_bins<NT>(z, mp, a.tws, tid, [&](int k, float re, float im) {
                     const float p = __fmaf_rn(re, re, im * im);
                     o[ob + (long long)k * a.T] = mag ? sqrt_approx(p) : p;
                 });
@@ -226,18 +227,18 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
             __syncthreads();                                            // the buffers are refilled by the next frame
             continue;
         }
-        mixed_bins(z, mp, a.tws, tid, [&](int k, float re, float im) { SST(&pw[padi(k)], __fmaf_rn(re, re, im * im)); });
+        mixed_bins<NT>(z, mp, a.tws, tid, [&](int k, float re, float im) { SST(&pw[padi(k)], __fmaf_rn(re, re, im * im)); });
         __syncthreads();
 
         float* const orow = a.out + (long long)u * a.n_rows * a.T + t;
         // ---------------- time-domain features (unwindowed, zero-padded frame) ----------------
         if (a.mask & syg::FB_TIME_ANY) {
-            const double tsq = group_sum<kThreads>(s_sq, dsc);
-            const float tpk = group_max<kThreads>(pk, dsc);
+            const double tsq = group_sum<NT>(s_sq, dsc);
+            const float tpk = group_max<NT>(pk, dsc);
             double tsum = 0.0, tabs = 0.0;
             if (a.mask & (syg::FB_STD_AMP | syg::FB_MEAN_AMP)) {
-                tsum = group_sum<kThreads>(s_sum, dsc);
-                tabs = group_sum<kThreads>(s_abs, dsc);
+                tsum = group_sum<NT>(s_sum, dsc);
+                tabs = group_sum<NT>(s_abs, dsc);
             }
             if (tid == 0) {
                 const double n = (double)N;
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
 
         // ---------------- per-frame spectral statistics: thread tid owns the contiguous bins [k0, k1) ----------------
         if (a.mask & syg::FB_SPECSTATS) {
-            const int chunk = (B + kThreads - 1) / kThreads;
+            const int chunk = (B + NT - 1) / NT;
             const int k0 = min(tid * chunk, B), k1 = min(k0 + chunk, B);
             double sp = 0.0, sm = 0.0, skm = 0.0, slog = 0.0;
             float vmax = -1.0f;
@@ -271,14 +272,14 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
                 if (a.mask & syg::FB_FLATNESS) slog += (double)logf(mg + 2.220446049250313e-16f);
                 if (p > vmax) { vmax = p; imax = k; }
             }
-            const double incl = group_scan_incl<kThreads>(sp, dsc);
+            const double incl = group_scan_incl<NT>(sp, dsc);
             __syncthreads();
             dinc[tid] = incl;
             __syncthreads();
-            const double total_p = dinc[kThreads - 1];
+            const double total_p = dinc[NT - 1];
             const double prev = (tid == 0) ? -1.0 : dinc[tid - 1];
-            const double tm = group_sum<kThreads>(sm, dsc);
-            const double tkm = group_sum<kThreads>(skm, dsc);
+            const double tm = group_sum<NT>(sm, dsc);
+            const double tkm = group_sum<NT>(skm, dsc);
             double centroid_hz = 0.0;
             if (tm >= kEps64) centroid_hz = a.bin_hz * (tkm / tm);
             if (a.row_centroid >= 0 && tid == 0) orow[(long long)a.row_centroid * a.T] = (float)centroid_hz;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
                 }
             }
             if (a.row_flatness >= 0) {
-                const double tl = group_sum<kThreads>(slog, dsc);
+                const double tl = group_sum<NT>(slog, dsc);
                 if (tid == 0) {
                     const double am = tm / (double)B;
                     double fl = 0.0;
@@ -317,21 +318,21 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
                     const double d = a.bin_hz * (double)k - centroid_hz;
                     sb += mg * d * d;
                 }
-                const double tb = group_sum<kThreads>(sb, dsc);
+                const double tb = group_sum<NT>(sb, dsc);
                 if (tid == 0) orow[(long long)a.row_bandwidth * a.T] = (tm < kEps64) ? 0.0f : (float)sqrt(tb / tm);
             }
             if (a.row_dominant >= 0) {
                 // np.argmax: first bin attaining the maximum = smallest index among the threads holding it
-                const float gmax = group_max<kThreads>(vmax, dsc);
+                const float gmax = group_max<NT>(vmax, dsc);
                 float mi = (vmax == gmax) ? -(float)imax : -1.0e9f;
-                mi = group_max<kThreads>(mi, dsc);
+                mi = group_max<NT>(mi, dsc);
                 if (tid == 0) orow[(long long)a.row_dominant * a.T] = (float)(a.bin_hz * (double)(-mi));
             }
         }
 
         // ---------------- mel energies (sparse triangular filters), one filter per thread ----------------
         if (a.mask & syg::FB_MFCC) {
-            for (int base = 0; base < a.n_mels; base += kThreads) {
+            for (int base = 0; base < a.n_mels; base += NT) {
                 const int m = base + tid;
                 float acc = 0.0f;
                 if (m < a.n_mels) {
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
         // ---------------- spectral contrast: per band mean of the n largest / n smallest magnitudes, one warp per band ----------------
         if (a.mask & syg::FB_CONTRAST) {
             float* mycand = cand + warp * 32;
-            for (int bd = warp; bd < a.nb; bd += kThreads / 32) {
+            for (int bd = warp; bd < a.nb; bd += NT / 32) {
                 const float peak = warp_extreme_mean_sqrt<+1>(pw, a.band_lo[bd], a.band_cnt[bd], a.band_n[bd], mycand);
                 const float valley = warp_extreme_mean_sqrt<-1>(pw, a.band_lo[bd], a.band_cnt[bd], a.band_n[bd], mycand);
                 if (lane == 0) {
@@ -380,10 +381,11 @@ __global__ void __launch_bounds__(kThreads) frame_mixed_kernel(const syg::FrameA
 // doubling except DC (and Nyquist when nfft is even).  The running sums live in the unit's own output row (every bin is always
 // visited by the same thread), so a 25 600-point periodogram needs shared memory for the two transform buffers only.
 // --------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) welch_mixed_kernel(const syg::WelchArgs a, const syg::MixedPlan mp) {
+template <int NT>
+__global__ void __launch_bounds__(NT) welch_mixed_kernel(const syg::WelchArgs a, const syg::MixedPlan mp) {
     SYG_DYN_SMEM(smem_raw);
     const int L = mp.L, B = mp.B;
-    const MixedLayout lay = mixed_layout(L, B, false);
+    const MixedLayout lay = mixed_layout(L, B, false, NT);
     float* const smf = reinterpret_cast<float*>(smem_raw);
     float2* const bufa = reinterpret_cast<float2*>(smf + lay.off_a);
     float2* const bufb = reinterpret_cast<float2*>(smf + lay.off_b);
@@ -398,11 +400,11 @@ __global__ void __launch_bounds__(kThreads) welch_mixed_kernel(const syg::WelchA
             float mean = 0.0f;
             if (a.detrend) {
                 double ssum = 0.0;
-                for (int i = tid; i < a.nperseg; i += kThreads) ssum += (double)load_one(a.y, ur, p0 + i, 0);
-                mean = (float)(group_sum<kThreads>(ssum, dsc) / (double)a.nperseg);
+                for (int i = tid; i < a.nperseg; i += NT) ssum += (double)load_one(a.y, ur, p0 + i, 0);
+                mean = (float)(group_sum<NT>(ssum, dsc) / (double)a.nperseg);
             }
             if (mp.packed) {
-                for (int c = tid; c < L; c += kThreads) {
+                for (int c = tid; c < L; c += NT) {
                     float2 v = make_float2(0.0f, 0.0f);
                     if (2 * c < a.nperseg) {
                         const float2 w = __ldg(reinterpret_cast<const float2*>(a.window) + c);
@@ -413,16 +415,16 @@ __global__ void __launch_bounds__(kThreads) welch_mixed_kernel(const syg::WelchA
                     SST(&bufa[c], v);
                 }
             } else {
-                for (int c = tid; c < L; c += kThreads) {
+                for (int c = tid; c < L; c += NT) {
                     float v = 0.0f;
                     if (c < a.nperseg) v = (load_one(a.y, ur, p0 + c, 0) - mean) * __ldg(a.window + c);
                     SST(&bufa[c], make_float2(v, 0.0f));
                 }
             }
             __syncthreads();
-            const float2* const z = mixed_fft(bufa, bufb, mp, a.tw, tid);
+            const float2* const z = mixed_fft<NT>(bufa, bufb, mp, a.tw, tid);
             const bool first = (s == 0);
-            mixed_bins(z, mp, a.tws, tid, [&](int k, float re, float im) {
+            mixed_bins<NT>(z, mp, a.tws, tid, [&](int k, float re, float im) {
                 const float p = __fmaf_rn(re, re, im * im);
                 prow[k] = first ? p : prow[k] + p;
             });
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) welch_mixed_kernel(const syg::WelchA
         }
         const float inv = a.scale / (float)a.nseg;
         const int nyq = (mp.n % 2 == 0) ? B - 1 : -1;
-        for (int k = tid; k < B; k += kThreads) {
+        for (int k = tid; k < B; k += NT) {
             float v = prow[k] * inv;
             if (a.onesided_double && k != 0 && k != nyq) v *= 2.0f;
             prow[k] = v;
@@ -438,13 +440,13 @@ __global__ void __launch_bounds__(kThreads) welch_mixed_kernel(const syg::WelchA
         if (a.stats) {
             double sq = 0.0;
             float pk = 0.0f;
-            for (long long i = tid; i < a.g.unit_len; i += kThreads) {
+            for (long long i = tid; i < a.g.unit_len; i += NT) {
                 const float v = (i < ur.valid) ? __ldg(a.y + ur.start + i) : 0.0f;
                 sq += (double)v * (double)v;
                 pk = fmaxf(pk, fabsf(v));
             }
-            const double tsq = group_sum<kThreads>(sq, dsc);
-            const float tpk = group_max<kThreads>(pk, dsc);
+            const double tsq = group_sum<NT>(sq, dsc);
+            const float tpk = group_max<NT>(pk, dsc);
             if (tid == 0) {
                 const double rms = a.g.unit_len > 0 ? sqrt(tsq / (double)a.g.unit_len) : 0.0;
                 a.stats[u * 3 + 0] = (float)rms;

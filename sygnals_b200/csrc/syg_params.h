@@ -15,7 +15,7 @@ __host__ __device__
 #endif
 inline int fin_pitch(int N) { int p = (N + 3) / 4 * 4; while ((p & 7) != 4) p += 4; return p; }
 
-// shared-memory layout (float words) of the mixed-radix kernels for L complex points and B bins
+// shared-memory layout (float words) of the mixed-radix kernels for L complex points, B bins and nt threads per CTA
 struct MixedLayout {
     int off_a, off_b, off_pw, off_cand, off_smax, off_dsc_f, total_f;
     size_t bytes;
@@ -23,15 +23,15 @@ struct MixedLayout {
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline MixedLayout mixed_layout(int L, int B, bool features) {
+inline MixedLayout mixed_layout(int L, int B, bool features, int nt = kThreads) {
     MixedLayout m;
     m.off_a = 0;
     m.off_b = 2 * L;
     m.off_pw = 4 * L;
     m.off_cand = m.off_pw + (features ? (B + (B >> 5) + 1) : 0);
-    m.off_smax = m.off_cand + (features ? (kThreads / 32) * 32 : 0);
+    m.off_smax = m.off_cand + (features ? (nt / 32) * 32 : 0);
     m.off_dsc_f = ((m.off_smax + 4 + 1) / 2) * 2;
-    m.total_f = m.off_dsc_f + 2 * (kThreads / 32 + kThreads);
+    m.total_f = m.off_dsc_f + 2 * (nt / 32 + nt);
     m.bytes = (size_t)m.total_f * 4;
     return m;
 }
