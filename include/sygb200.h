@@ -221,6 +221,10 @@ int syg_spectral_contrast_from_mag_f32(syg_ctx* ctx, const float* S_dev, int32_t
 /* which kernel family the last syg_stft_* call of this process launched: 1 TMA-staged ring kernel, 2 register-staged warp
  * kernel, 3 CTA-cooperative kernels, 4 sub-FFT kernel for n_fft 4096 / 8192 (tests and bench.py report it) */
 int syg_debug_last_stft_path(void);
+/* 1 when the last feature launch kept its (short) units on chip: mel tile + dB + DCT inside the frame kernel, no finalize launch */
+int syg_debug_last_features_resident(void);
+/* unit groups a launch needs before the resident kernel is chosen (default -1: four per SM); tests set 1 to drive it with few units */
+void syg_debug_set_resident_min_groups(int n);
 int syg_debug_window(int32_t window, int32_t win_length, int32_t n_fft, float* out);
 int syg_debug_mel_basis(int32_t sr, int32_t n_fft, int32_t n_mels, double fmin, double fmax, float* out);
 int syg_debug_dct(int32_t n_mfcc, int32_t n_mels, int32_t dct_type, int32_t ortho, double lifter, float* out);

@@ -293,6 +293,7 @@ int launch_features(int n_fft, const syg::FrameArgs& a_in, int sm_count, cudaStr
         return launch_rc(syglaunch::frame_mixed(sygdev::MODE_FEATURES, a, mp, sm_count, st, err), err);
     }
     if (n_fft > 2048) return launch_rc(syglaunch::frame_block(n_fft, sygdev::MODE_FEATURES, a, sm_count, st, err), err);
+    if (a.res_units > 0) return launch_rc(syglaunch::frame_warp_res(n_fft, a, sm_count, st, err), err);
     constexpr unsigned extra = syg::FB_BANDWIDTH | syg::FB_FLATNESS | syg::FB_DOMINANT | syg::FB_MEAN_AMP | syg::FB_STD_AMP;
     return launch_rc(syglaunch::frame_warp(n_fft, (a.mask & extra) != 0, a, sm_count, st, err), err);
 }
@@ -302,6 +303,8 @@ int warp_fw(int n_fft) {
     switch (ilog2i(n_fft / 2)) { case 4: return 8; case 5: return 8; case 6: return 4; case 7: return 4; case 8: return 2; case 9: return 2; default: return 1; }
 }
 
+int g_resident_min_groups = -1;     // unit groups a launch needs before the resident kernel is chosen (-1: 4 per SM); tests lower it
+int g_last_features_resident = 0;   // 1: the last feature launch kept its units on chip (frame_warp_kernel STAGE 5)
 int g_last_stft_path = 0;   // 5 mixed-radix kernel (lengths that are not powers of two), 1 ring (TMA-staged), 2 warp kernel (register-staged), 3 CTA-cooperative kernels, 4 sub-FFT kernel (n_fft 4096 / 8192): last STFT launch
 
 int launch_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st) {
@@ -574,7 +577,29 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
     a.melws = reinterpret_cast<float*>(w + off);
     off += ((size_t)a.n_frames * pl.fin.n_mels * sizeof(float) + 255) / 256 * 256;
     a.cws = reinterpret_cast<float*>(w + off);
-    const bool need_fin = (a.mask & (syg::FB_MFCC | syg::FB_CONTRAST)) != 0;
+    // Short units with an MFCC-only epilogue stay on chip (frame_warp_kernel STAGE 5): no mel workspace, no finalize launch.  Needs
+    // enough unit groups to fill the GPU; SYGB200_NO_RES=1 keeps the two-kernel path (A/B measurements).
+    {
+        static int no_res = -1;
+        if (no_res < 0) { const char* e = std::getenv("SYGB200_NO_RES"); no_res = e ? std::atoi(e) : 0; }
+        constexpr unsigned other = syg::FB_CONTRAST | syg::FB_BANDWIDTH | syg::FB_FLATNESS | syg::FB_DOMINANT | syg::FB_MEAN_AMP | syg::FB_STD_AMP;
+        a.res_units = 0;
+        if (!no_res && (a.mask & syg::FB_MFCC) && !(a.mask & other) && native_pow2(n_fft) && n_fft <= 1024) {
+            const int ku = syglaunch::frame_warp_res_units(n_fft, a);
+            const long long min_groups = g_resident_min_groups >= 0 ? g_resident_min_groups : 4LL * ctx->sm_count;
+            if (ku > 0 && (g.n_units + ku - 1) / ku >= min_groups) {
+                a.res_units = ku;
+                a.fin_dct = pl.fin.dct;
+                a.fin_n_mfcc = pl.fin.n_mfcc;
+                a.fin_row_mfcc = pl.fin.row_mfcc;
+                a.fin_dct_fold = pl.fin.dct_fold;
+                a.fin_amin = pl.fin.amin;
+                a.fin_top_db = pl.fin.top_db;
+            }
+        }
+    }
+    g_last_features_resident = a.res_units > 0 ? 1 : 0;
+    const bool need_fin = (a.mask & (syg::FB_MFCC | syg::FB_CONTRAST)) != 0 && a.res_units == 0;
     if (need_fin) CK(cudaMemsetAsync(a.unit_max, 0, (size_t)g.n_units * 4 * sizeof(unsigned), st));
     int rc = SYG_OK;
     if (a.mask & syg::FB_TIME_EXTRA) {                                  // zcr / skewness / kurtosis / entropy: their own streaming kernel
@@ -1326,6 +1351,8 @@ int syg_spectral_contrast_from_mag_f32(syg_ctx* ctx, const float* S_dev, int32_t
 }
 
 int syg_debug_last_stft_path(void) { return g_last_stft_path; }
+int syg_debug_last_features_resident(void) { return g_last_features_resident; }
+void syg_debug_set_resident_min_groups(int n) { g_resident_min_groups = n; }
 
 int syg_debug_window(int32_t window, int32_t win_length, int32_t n_fft, float* out) {
     if (!out) return fail(SYG_E_BADARG, "out is NULL");

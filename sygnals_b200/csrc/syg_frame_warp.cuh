@@ -21,6 +21,7 @@
 #include "syg_device.cuh"
 #include "syg_kernels.cuh"
 #include "syg_params.h"
+#include "syg_finalize_dev.cuh"
 
 namespace sygdev {
 
@@ -48,7 +49,7 @@ struct WarpTile {
     // plan tables kept in shared memory by the fused kernel (all 16-byte multiples): window [2M] floats, tw [M] float2,
     // twsh [M/2+1] float2, mel slots [n_mels] int4, mel taps [mel_pw_f4] float4
     static constexpr int kWinB = 2 * M * 4, kTwB = M * 8, kTwshB = ((M / 2 + 1) * 8 + 15) / 16 * 16;
-    static size_t table_bytes(int n_mels, int mel_pw_f4) { return (size_t)kWinB + kTwB + kTwshB + (size_t)n_mels * 16 + (size_t)mel_pw_f4 * 16; }
+    SYG_HD static size_t table_bytes(int n_mels, int mel_pw_f4) { return (size_t)kWinB + kTwB + kTwshB + (size_t)n_mels * 16 + (size_t)mel_pw_f4 * 16; }
 };
 
 template <int LOG2E>
@@ -120,6 +121,11 @@ SYG_DEVICE SYG_INLINE double lanes_scan_incl(double v, int gl) {
 // STAGE 3: STFT output (framing -> FFT -> real split -> transposed CTA tile -> contiguous row stores).
 // STAGE 4: STFT magnitude / power output for M <= 256 (n_fft <= 512): every WARP owns 8 consecutive frames and a private transposed
 //          tile [B][8 + 1] -- no CTA barrier at all, the warps of an SM drift apart and overlap each other's load / FFT / store phases.
+// STAGE 5: STAGE 0 for SHORT units with the MFCC epilogue on chip (BASELINE cfg3: T = 101 frames, 40 mel bands).  A CTA owns groups of
+//          `res_units` consecutive units; the raw mel energies of a group's frames stay in a shared-memory tile, the per-unit maxima
+//          in shared words, and after the group's last frame the CTA applies power_to_db(ref = unit max, top_db) and the DCT (FP64
+//          DMMA, the code of finalize_kernel) in place and writes the MFCC rows: no mel workspace round trip through HBM, no
+//          finalize launch.  Two CTAs per SM alternate between their transform and their epilogue phases.
 // (A two-launch variant -- FFT kernel + 64-register epilogue kernel with the spectra handed over through a workspace -- was
 // measured and removed: +4 % at best, see DESIGN.md 4.1 and profiles/r01_t_two_stage_ncu_summary.txt.  CTA barriers between
 // the phases of the fused kernel were measured too: +8 % time.)
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     // warps' regions -- 116 table loads per lane and frame become LDS with no L1 tag traffic and no misses
     // STAGE 4 keeps window / twiddles / (full-scale) split twiddles there too, behind the per-warp tile blocks: its L1 pipe is the
     // busiest unit (95 %) and 40 of its 56 loads per lane and task were table reads through the L1 tag stage
-    constexpr bool TBL = (STAGE == 0 || STAGE == 4);
+    constexpr bool TBL = (STAGE == 0 || STAGE == 4 || STAGE == 5);
     unsigned char* const tb = smem_raw + ((size_t)WT::kWarps * WF + (STAGE == 4 ? (size_t)WT::kWarps * WB4 : 0)) * sizeof(float);
     const float2* const t_win = TBL ? reinterpret_cast<const float2*>(tb) : reinterpret_cast<const float2*>(a.window);
     const float2* const t_tw = TBL ? reinterpret_cast<const float2*>(tb + WT::kWinB) : a.tw;
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         for (int i = tid; i < M; i += NT) d_tw[i] = __ldg(a.tw + (i / E) * (i % E));
         float2* d_twsh = const_cast<float2*>(t_twsh);
         for (int i = tid; i <= M / 2; i += NT) d_twsh[i] = __ldg((STAGE == 4 ? a.tws : a.twsh) + i);
-        if (STAGE == 0 && (a.mask & syg::FB_MFCC)) {
+        if ((STAGE == 0 || STAGE == 5) && (a.mask & syg::FB_MFCC)) {
             int4* d_sl = const_cast<int4*>(t_slots);
             for (int i = tid; i < a.n_mels; i += NT) d_sl[i] = __ldg(a.mel_slots + i);
             float4* d_mw = const_cast<float4*>(t_melw);
@@ -184,27 +190,48 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         __syncthreads();
     }
 
+    // STAGE 5: behind the tables: tile [GF8][P] of raw mel energies (then S_db), per-frame reference levels and output offsets, per-unit maxima
+    constexpr bool RES = (STAGE == 5);
+    const int res_P = RES ? fin_pitch(a.n_mels) : 0;
+    const int res_GF8 = RES ? (a.res_units * a.T + 7) / 8 * 8 : 0;
+    float* const res_tile = reinterpret_cast<float*>(tb + (RES ? WT::table_bytes(a.n_mels, (a.mask & syg::FB_MFCC) ? a.mel_pw_f4 : 0) : 0));
+    float* const res_ref = res_tile + (size_t)res_GF8 * res_P;
+    long long* const res_out = reinterpret_cast<long long*>(res_ref + res_GF8);          // res_GF8 is even: 8-byte aligned
+    unsigned* const res_umax = reinterpret_cast<unsigned*>(res_out + res_GF8);
+
     const long long n_tasks = (a.n_frames + FW - 1) / FW;
     // (unit, frame-in-unit) of this lane's frame advance incrementally: one division per kernel instead of one per frame
-    const long long stride_tasks = (long long)gridDim.x * WT::kWarps;
+    const long long stride_tasks = RES ? WT::kWarps : (long long)gridDim.x * WT::kWarps;
     // STAGE 4 walks "super tasks" of 8 consecutive frames (SUBS tasks each) per warp: small steps of FW frames inside one, a
     // large step to the warp's next super task
     const long long stride_frames = (STAGE == 4) ? (stride_tasks - 1) * TT4 + FW : stride_tasks * FW;
     const long long du = stride_frames / a.T;
     const int dt = (int)(stride_frames - du * a.T);
-    long long gf_run = ((long long)blockIdx.x * WT::kWarps + warp) * ((STAGE == 4) ? TT4 : FW) + f;
+    // STAGE 5: outer loop over this CTA's unit groups (every other stage: one pass)
+    const long long n_groups = RES ? (a.g.n_units + a.res_units - 1) / a.res_units : 1;
+    for (long long grp = RES ? blockIdx.x : 0; grp < n_groups; grp += RES ? gridDim.x : 1) {
+    const long long grp_u0 = RES ? grp * a.res_units : 0;
+    const long long grp_f0 = grp_u0 * a.T;                             // first frame of the group
+    const long long frame_end = RES ? min(grp_u0 + a.res_units, a.g.n_units) * (long long)a.T : a.n_frames;
+    if (RES) {
+        if (tid < a.res_units) res_umax[tid] = 0u;
+        __syncthreads();
+    }
+    long long gf_run = RES ? grp_f0 + (long long)warp * FW + f
+                           : ((long long)blockIdx.x * WT::kWarps + warp) * ((STAGE == 4) ? TT4 : FW) + f;
     long long u_run = gf_run / a.T;
     int t_run = (int)(gf_run - u_run * a.T);
-    const long long task_begin = (STAGE == 4) ? ((long long)blockIdx.x * WT::kWarps + warp) * SUBS : (long long)blockIdx.x * WT::kWarps;
-    const long long task_end = (STAGE == 4) ? ((a.n_frames + TT4 - 1) / TT4) * SUBS : n_tasks;
-    // STAGE 0 / 3: all warps of the CTA run the same number of iterations (tasks past the end are processed as empty frames)
+    const long long task_begin = (STAGE == 4) ? ((long long)blockIdx.x * WT::kWarps + warp) * SUBS : (RES ? 0 : (long long)blockIdx.x * WT::kWarps);
+    const long long task_end = (STAGE == 4) ? ((a.n_frames + TT4 - 1) / TT4) * SUBS : (RES ? (frame_end - grp_f0 + FW - 1) / FW : n_tasks);
+    // STAGE 0 / 3 / 5: all warps of the CTA run the same number of iterations (tasks past the end are processed as empty frames)
     for (long long task0 = task_begin; task0 < task_end;
          task0 = (STAGE == 4) ? ((((task0 + 1) & (SUBS - 1)) != 0) ? task0 + 1 : task0 + 1 + (stride_tasks - 1) * SUBS) : task0 + stride_tasks) {
         const long long task = (STAGE == 4) ? task0 : task0 + warp;
+        const long long tf0 = RES ? grp_f0 + task * FW : task * FW;    // first global frame of this warp's task
         // (measured in round 2: re-aligning the warps of one scheduler with a named barrier once per frame, so that they share
         // instruction fetches of the ~50 KB loop body, costs +2.4 % -- the phase diversity is worth more than the fetches)
         const long long gf = gf_run;
-        const bool valid = gf < a.n_frames;
+        const bool valid = gf < frame_end;
         const long long u = valid ? u_run : 0;
         const int t = valid ? t_run : 0;
         if (STAGE == 4 && ((task0 + 1) & (SUBS - 1)) != 0) {          // next task of the same super task: FW frames on
@@ -596,8 +623,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         // ---------------- spectral contrast: per band mean of the n largest / n smallest magnitudes ----------------
         if (a.mask & syg::FB_CONTRAST) {
             for (int ff = 0; ff < FW; ++ff) {
-                const long long gff = task * FW + ff;
-                if (gff >= a.n_frames) break;
+                const long long gff = tf0 + ff;
+                if (gff >= frame_end) break;
                 const float* pp = pww + ff * RSS;
                 float pmx = 0.0f, vmx = 0.0f;
                 float mine_pv = 0.0f;                                   // lane bd keeps band bd's peak, lane nb + bd its valley
@@ -637,8 +664,10 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         if (a.mask & syg::FB_MFCC) {
             constexpr int GS = 32 / FW;
             const int mf = lane / GS, sl = lane % GS;                   // frame of the warp task, slot within the sweep group
-            const long long gmf = task * FW + mf;
-            const bool fvalid = gmf < a.n_frames;
+            const long long gmf = tf0 + mf;
+            const bool fvalid = gmf < frame_end;
+            // STAGE 5: the energies stay in the CTA tile (row = frame within the group)
+            float* const mrow = RES ? res_tile + (size_t)(gmf - grp_f0) * res_P : a.melws + gmf * a.n_mels;
             const float* pfr = pww + mf * RSS;
             const float4* const mw4 = t_melw;
             float fmx = 0.0f;
@@ -690,7 +719,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     const int4 pk4 = picks[m];                          // {r0, r1, f0, f1}
                     const float acc = (reg[pk4.x] + reg[pk4.y]) + (reg[pk4.z] + reg[pk4.w]);
                     if (fvalid) {
-                        a.melws[gmf * a.n_mels + m] = acc;
+                        mrow[m] = acc;
                         fmx = fmaxf(fmx, acc);
                     }
                 }
@@ -713,7 +742,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     }
                     const float acc = (m01.x + m01.y) + (m23.x + m23.y);
                     if (fvalid) {
-                        a.melws[gmf * a.n_mels + d.x] = acc;
+                        mrow[d.x] = acc;
                         fmx = fmaxf(fmx, acc);
                     }
                     goff += 32 * SP::steps(sw);
@@ -761,16 +790,90 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     }
                 }
                 if (base + sl < a.n_mels && fvalid) {
-                    a.melws[gmf * a.n_mels + d.x] = acc;
+                    mrow[d.x] = acc;
                     fmx = fmaxf(fmx, acc);
                 }
             }
             const float gmx = lanes_max<GS>(fmaxf(fmx, 0.0f));
             const long long umf = __shfl_sync(kFull, u, mf * G);       // unit of frame mf (all lanes take part)
-            if (sl == 0 && fvalid && gmx > 0.0f) atomicMax(&a.unit_max[umf * 4 + 0], __float_as_uint(gmx));
+            if (sl == 0 && fvalid && gmx > 0.0f) {
+                if (RES) atomicMax(&res_umax[(int)(umf - grp_u0)], __float_as_uint(gmx));
+                else atomicMax(&a.unit_max[umf * 4 + 0], __float_as_uint(gmx));
+            }
         }
 
         __syncwarp();                                                   // smem slices are reused by the next task
+    }
+    if constexpr (RES) {
+        // ---------------- the group's MFCC epilogue, on chip (finalize_kernel's arithmetic on the shared-memory tile) ----------------
+        __syncthreads();
+        const int gfr = (int)(frame_end - grp_f0);                      // frames of this group
+        const int N = a.n_mels, P = res_P;
+        for (int fi = tid; fi < gfr; fi += NT) {
+            const int ul = fi / a.T, tt = fi - ul * a.T;
+            res_ref[fi] = db10(fmaxf(a.fin_amin, __uint_as_float(res_umax[ul])));
+            res_out[fi] = (grp_u0 + ul) * (long long)a.n_rows * a.T + tt;
+        }
+        __syncthreads();
+        {
+            // A warp item = 8 consecutive frames, BOTH parities (two independent DMMA chains per k-step).  The dB conversion of
+            // power_to_db happens on the way into the B fragment: every tile entry is read and converted exactly once.
+            const int H = a.fin_dct_fold ? (N + 1) / 2 : N;
+            const int H4 = (H + 3) / 4 * 4;
+            const int g = lane >> 2, q = lane & 3;
+            const int n8 = (gfr + 7) / 8;
+            const float floor_db = -a.fin_top_db;
+            for (int w = warp; w < n8; w += WT::kWarps) {
+                const int nt8 = w * 8;
+                const int fr = min(nt8 + g, gfr - 1);                   // this lane's frame (B column); the tail tile repeats the last frame
+                const float* const xrow = res_tile + (size_t)fr * P;
+                const float ref_db = res_ref[fr];
+                const int t0 = nt8 + 2 * q;
+                const long long o0 = (t0 < gfr) ? res_out[t0] : 0, o1 = (t0 + 1 < gfr) ? res_out[t0 + 1] : 0;
+                const int n_even = (a.fin_n_mfcc + 1) / 2;
+                for (int m0 = 0; m0 < n_even; m0 += 8) {
+                    const int c_e = 2 * (m0 + g), c_o = c_e + 1;        // coefficients of this lane's A rows (even / odd parity)
+                    const bool e_ok = c_e < a.fin_n_mfcc, o_ok = c_o < a.fin_n_mfcc;
+                    const double* const drow_e = a.fin_dct + (long long)(e_ok ? c_e : 0) * N + q;
+                    const double* const drow_o = a.fin_dct + (long long)(o_ok ? c_o : 0) * N + q;
+                    double e0 = 0.0, e1 = 0.0, d0 = 0.0, d1 = 0.0;
+                    for (int k0 = 0; k0 < H4; k0 += 4) {
+                        const int k = k0 + q;
+                        const bool k_ok = k < H;
+                        const double av_e = (e_ok && k_ok) ? __ldg(drow_e + k0) : 0.0;
+                        const double av_o = (o_ok && k_ok) ? __ldg(drow_o + k0) : 0.0;
+                        double bs = 0.0, bd = 0.0;                      // folded: s[k] + s[N-1-k] for even rows, s[k] - s[N-1-k] for odd rows
+                        if (k_ok) {
+                            const float x = fmaxf(db10(fmaxf(a.fin_amin, xrow[k])) - ref_db, floor_db);
+                            bs = bd = (double)x;
+                            if (a.fin_dct_fold) {
+                                const int k2 = N - 1 - k;
+                                if (k2 != k) {
+                                    const float x2 = fmaxf(db10(fmaxf(a.fin_amin, xrow[k2])) - ref_db, floor_db);
+                                    bs = (double)x + (double)x2;
+                                    bd = (double)x - (double)x2;
+                                } else {
+                                    bd = 0.0;                           // centre of an odd N: once, even rows only
+                                }
+                            }
+                        }
+                        mma_m8n8k4_f64(e0, e1, av_e, bs);
+                        mma_m8n8k4_f64(d0, d1, av_o, bd);
+                    }
+                    // lane holds coefficient c of frames nt8 + 2q, nt8 + 2q + 1
+                    if (e_ok) {
+                        if (t0 < gfr) a.out[o0 + (long long)(a.fin_row_mfcc + c_e) * a.T] = (float)e0;
+                        if (t0 + 1 < gfr) a.out[o1 + (long long)(a.fin_row_mfcc + c_e) * a.T] = (float)e1;
+                    }
+                    if (o_ok) {
+                        if (t0 < gfr) a.out[o0 + (long long)(a.fin_row_mfcc + c_o) * a.T] = (float)d0;
+                        if (t0 + 1 < gfr) a.out[o1 + (long long)(a.fin_row_mfcc + c_o) * a.T] = (float)d1;
+                    }
+                }
+            }
+        }
+        __syncthreads();                                                // the tile is refilled by the next group
+    }
     }
 }
 

@@ -13,6 +13,9 @@ int frame_warp(int n_fft, bool extra, const syg::FrameArgs& a, int sm_count, cud
 int stft_ring(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 // n_fft 4096 / 8192, real-valued output: 1024-point sub-FFTs per warp + recombination (syg_stft_big.cuh)
 int stft_big(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
+// unit-resident feature kernel (short units, MFCC epilogue on chip): units per CTA group for this plan (0 = not eligible), launch
+int frame_warp_res_units(int n_fft, const syg::FrameArgs& a);
+int frame_warp_res(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 int frame_warp_stft(int n_fft, const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 int finalize(const syg::FinalizeArgs& a, int tt, unsigned grid_x, unsigned grid_y, size_t smem, cudaStream_t st, std::string& err);
 int aggregate(const float* feats, long long n_seg, int n_rows, long long row_stride, const long long* seg_off, const int* seg_len,

@@ -106,6 +106,11 @@ struct FrameArgs {
     int mel_nsweeps;            // sweeps of the warp kernel's mel plan and their float4 step counts (host side: lets the launcher
     int mel_steps[8];           // pick a plan-specialised kernel); 0 sweeps = not recorded
     int variant;                // measurement switch (SYGB200_VARIANT, default 0): bit 0 = per-scheduler lock step (see frame_warp_kernel)
+    // ---- unit-resident MFCC epilogue (frame_warp_kernel STAGE 5): the finalize arguments + units per CTA group
+    int res_units;
+    const double* fin_dct;
+    int fin_n_mfcc, fin_row_mfcc, fin_dct_fold;
+    float fin_amin, fin_top_db;
     // ---- stft
     int out_kind;               // 0 complex64, 1 magnitude, 2 power
     void* stft_out;             // [n_units][B][T]

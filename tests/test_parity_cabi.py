@@ -298,7 +298,7 @@ def test_empty_and_errors(eng):
     out = eng.features_host(np.zeros(100, np.float32), eng.units_clips(1, 100), p2)
     assert out.shape == (1, 1, 0)
     with pytest.raises(NotImplementedError):
-        eng.features_host(np.zeros(4000, np.float32), eng.units_clips(1, 4000), _ffi.make_params(eng.lib, 16000, ["mfcc"], 1000, 160))
+        eng.features_host(np.zeros(4000, np.float32), eng.units_clips(1, 4000), _ffi.make_params(eng.lib, 16000, ["mfcc"], 1006, 160))   # 2 * 503: no kernel for this length
     with pytest.raises(ValueError):
         eng.features_host(np.zeros(4000, np.float32), eng.units_clips(1, 4000),
                           _ffi.make_params(eng.lib, 16000, ["mfcc"], 512, 160, feature_params={"mfcc": {"n_mfcc": 200}}))
