@@ -270,6 +270,34 @@ SYG_DEVICE SYG_INLINE void split_power(float2 zk, float2 zm, float2 wh, float& p
 }
 
 // --------------------------------------------------------------------------------------------------------
+// Mirror exchange of the real split by warp shuffles (two-pass warp tiles: R2 = G, Q = E / G).
+// After pass 2 the lane j of a frame's G lanes holds Z[j + G m], m < E, in register zreg_of(m).  The split pairs bin
+// k = j + G m with M - k = (G - j) + G (E - 1 - m): the mirror of a lane's lower half (m < E/2) is the UPPER half of lane
+// G - j, register zreg_of(E - 1 - m) -- the same register in every lane, so one SHFL per word moves it.  Lane 0 is the one
+// exception (M - G m = G (E - m): its own register zreg_of(E - m), m = 0 pairing with itself for DC / Nyquist): it selects
+// that register before the shuffle and reads from itself.  Replaces the natural-order store of Z and the two strided loads of
+// the split (E STS.64 + (E + 2) LDS.64 per lane: >= 4 E shared-memory wavefronts per warp task) by E SEL + E SHFL.
+// --------------------------------------------------------------------------------------------------------
+#ifndef SYG_SPLIT_SHFL
+#define SYG_SPLIT_SHFL 1
+#endif
+template <int E, int G>
+SYG_HD constexpr int zreg_of(int m) { return (m % (E / G)) * G + bitrev(m / (E / G), ilog2(G)); }
+
+template <int E, int G>
+SYG_DEVICE SYG_INLINE float2 mirror_of(const float2* z, int m, int j) {     // Z[M - (j + G m)], 0 <= m < E/2 (m: compile time)
+    const float2 a = z[zreg_of<E, G>((E - m) % E)];
+    const float2 b = z[zreg_of<E, G>(E - 1 - m)];
+    const bool l0 = (j == 0);
+    const float sx = l0 ? a.x : b.x, sy = l0 ? a.y : b.y;
+    const int src = (G - j) & (G - 1);
+    float2 r;
+    r.x = __shfl_sync(kFull, sx, src, G);
+    r.y = __shfl_sync(kFull, sy, src, G);
+    return r;
+}
+
+// --------------------------------------------------------------------------------------------------------
 // thread-group collectives.  Groups are G consecutive threads (G a power of two, 1..kThreads); every thread of
 // the CTA calls them (lock step).  scratch: kThreads/32 doubles of shared memory.
 // --------------------------------------------------------------------------------------------------------

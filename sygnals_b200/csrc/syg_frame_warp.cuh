@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, ZS = WT::ZS, PS = WT::PS, LE = WT::LOG2E;
     constexpr int Q = E / R2;
     constexpr int B = M + 1;
+    static_assert(R2 == G, "two-pass warp tile: the last radix equals the lanes per frame");
+    constexpr bool kShflSplit = (SYG_SPLIT_SHFL != 0);                  // mirrors of the real split by SHFL (syg_device.cuh: mirror_of)
     SYG_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -338,13 +340,15 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
             }
             dft_dif_p<R2, 1>(z + q * R2);
-            const int ob = (b - k) * R2 + k;
-            SYG_UNROLL
-            for (int kp = 0; kp < R2; ++kp) {
-                zs[zpad<LE>(ob + kp * E)] = z[q * R2 + bitrev(kp, ilog2(R2))];
+            if constexpr (!kShflSplit) {
+                const int ob = (b - k) * R2 + k;
+                SYG_UNROLL
+                for (int kp = 0; kp < R2; ++kp) {
+                    zs[zpad<LE>(ob + kp * E)] = z[q * R2 + bitrev(kp, ilog2(R2))];
+                }
             }
         }
-        __syncwarp();
+        if constexpr (!kShflSplit) __syncwarp();
 
         // ---------------- real split -> |X[k]|^2 (overwrites the Z region: all pairs are pulled into registers first) ----------------
         // Lane j pairs bin k = j + i G with bin M - k.  All addresses are lane bases plus compile-time offsets: for j >= 1
@@ -356,16 +360,26 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             const float2* const zm0 = zs - j;                           // Z[M - k] at zm0[c1_i], lane 0: + 1 where M - iG starts a block
             const float2* const zm1 = zm0 + jz;
             float2 zk[E / 2 + 1], zm[E / 2 + 1];
-            SYG_UNROLL
-            for (int i = 0; i <= E / 2; ++i) {
-                const int kk = i * G;                                    // compile time after unrolling
-                zk[i] = zk0[kk + (kk >> LE)];
-                const int c1 = (M - kk) + ((M - kk - 1) >> LE);          // zpad(M - kk - j) + j for 1 <= j < G
-                const bool blk = ((M - kk) & (E - 1)) == 0;              // M - kk starts a pad block -> lane 0 is one slot further
-                zm[i] = blk ? zm1[c1] : zm0[c1];
+            if constexpr (kShflSplit) {
+                // the mirrors come from the partner lane's registers (mirror_of): no natural-order Z in shared memory at all
+                SYG_UNROLL
+                for (int i = 0; i < E / 2; ++i) {
+                    zk[i] = z[zreg_of<E, G>(i)];
+                    zm[i] = mirror_of<E, G>(z, i, j);
+                }
+                zk[E / 2] = zm[E / 2] = z[zreg_of<E, G>(E / 2)];          // lane 0 only: bin M/2 pairs with itself
+            } else {
+                SYG_UNROLL
+                for (int i = 0; i <= E / 2; ++i) {
+                    const int kk = i * G;                                // compile time after unrolling
+                    zk[i] = zk0[kk + (kk >> LE)];
+                    const int c1 = (M - kk) + ((M - kk - 1) >> LE);      // zpad(M - kk - j) + j for 1 <= j < G
+                    const bool blk = ((M - kk) & (E - 1)) == 0;          // M - kk starts a pad block -> lane 0 is one slot further
+                    zm[i] = blk ? zm1[c1] : zm0[c1];
+                }
+                if (j == 0) zm[0] = zk[0];                               // k = 0 pairs with itself (DC / Nyquist)
+                __syncwarp();
             }
-            if (j == 0) zm[0] = zk[0];                                   // k = 0 pairs with itself (DC / Nyquist)
-            __syncwarp();
             float* const pk0 = pf + j;                                   // P[k]     at pk0[ppad(iG)]
             float* const pm0 = pf - j;                                   // P[M - k] at pm0[q1_i], lane 0: + 4 where M - iG starts a 32-bin block
             float* const pm1 = pm0 + 4 * jz;

@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
     using WT = typename RG::WT;
     constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, LE = WT::LOG2E;
     constexpr int Q = E / R2, B = M + 1, NT = RG::NT, TT = RG::TT, TTP = RG::TTP, RSS = RG::RSR, WF = RG::WF;
+    static_assert(R2 == G, "two-pass warp tile");
+    constexpr bool kShflSplit = (SYG_SPLIT_SHFL != 0);                  // mirrors of the real split by SHFL (syg_device.cuh: mirror_of)
     SYG_DYN_SMEM(smem_raw);
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw);          // [S] "stage full"
     float* const fb = reinterpret_cast<float*>(smem_raw + RG::kBarBytes);
@@ -187,11 +189,13 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
                 cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
             }
             dft_dif_p<R2, 1>(z + q * R2);
-            const int ob = (b - k) * R2 + k;
-            SYG_UNROLL
-            for (int kp = 0; kp < R2; ++kp) zs[zpad<LE>(ob + kp * E)] = z[q * R2 + bitrev(kp, ilog2(R2))];
+            if constexpr (!kShflSplit) {
+                const int ob = (b - k) * R2 + k;
+                SYG_UNROLL
+                for (int kp = 0; kp < R2; ++kp) zs[zpad<LE>(ob + kp * E)] = z[q * R2 + bitrev(kp, ilog2(R2))];
+            }
         }
-        __syncwarp();
+        if constexpr (!kShflSplit) __syncwarp();
 
         // ---------------- real split -> |X| or |X|^2 -> transposed tile ----------------
         if (!DB) __syncthreads();                                                              // the single tile has been drained by everyone
@@ -206,11 +210,18 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
                 const int kk = ii * G;
                 const int k = j + kk;
                 if (ii == E / 2 && j != 0) break;
-                const float2 zk = zk0[kk + (kk >> LE)];
-                const int c1 = (M - kk) + ((M - kk - 1) >> LE);
-                const bool blk = ((M - kk) & (E - 1)) == 0;
-                float2 zm = blk ? zm1[c1] : zm0[c1];
-                if (ii == 0 && j == 0) zm = zk;                                                // k = 0 pairs with itself (DC / Nyquist)
+                float2 zk, zm;
+                if constexpr (kShflSplit) {                                                    // mirrors from the partner lane's registers
+                    zk = z[zreg_of<E, G>(ii)];
+                    zm = zk;                                                                   // ii = E/2 (lane 0): bin M/2 pairs with itself
+                    if (ii < E / 2) zm = mirror_of<E, G>(z, ii, j);
+                } else {
+                    zk = zk0[kk + (kk >> LE)];
+                    const int c1 = (M - kk) + ((M - kk - 1) >> LE);
+                    const bool blk = ((M - kk) & (E - 1)) == 0;
+                    zm = blk ? zm1[c1] : zm0[c1];
+                    if (ii == 0 && j == 0) zm = zk;                                            // k = 0 pairs with itself (DC / Nyquist)
+                }
                 float pk_, pm_;
                 split_power(zk, zm, t_twsh[k], pk_, pm_);
                 if (a.out_kind == 1) { pk_ = sqrt_approx(pk_); pm_ = sqrt_approx(pm_); }

@@ -38,6 +38,15 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
     using WW = WelchWarpTile<TL, NT, TBLW>;
     constexpr int E = WT::E, M = WT::M, G = WT::G, FW = WT::FW, R2 = WT::R2, PS = WW::PS, LE = WT::LOG2E;
     constexpr int Q = E / R2;
+    static_assert(R2 == G, "two-pass warp tile");
+    constexpr bool kShflSplit = (SYG_SPLIT_SHFL != 0);                  // mirrors of the real split by SHFL (syg_device.cuh: mirror_of)
+#ifndef SYG_WELCH_REGACC
+#define SYG_WELCH_REGACC 0
+#endif
+    // With the shuffle split a lane produces the SAME bins (k = j + G i and M - k) for every sub-segment, so their running sums
+    // could stay in registers (E + 1 floats; same additions in the same order: bit-identical).  Measured on B200 (cfg5, nfft 1024):
+    // 2.91 ms against 2.78 ms with the shared-memory accumulator -- at 128 registers the extra 33 live values spill.  Off.
+    constexpr bool kRegAcc = kShflSplit && (SYG_WELCH_REGACC != 0);
     constexpr int B = M + 1;
     SYG_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x;
@@ -69,8 +78,16 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
     for (long long u = (long long)blockIdx.x * WT::kWarps + warp; u < a.g.n_units; u += warps) {
         const UnitRef ur = unit_ref(a.g, u);
         const float* yb = a.y + ur.start;
-        for (int i = lane; i < FW * PS; i += 32) accw[i] = 0.0f;
-        __syncwarp();
+        float ak[E / 2 + 1], am[E / 2];                                // kRegAcc: sums of |X[j + G i]|^2 and of the mirrors |X[M - j - G i]|^2
+        if constexpr (kRegAcc) {
+            SYG_UNROLL
+            for (int i = 0; i <= E / 2; ++i) ak[i] = 0.0f;
+            SYG_UNROLL
+            for (int i = 0; i < E / 2; ++i) am[i] = 0.0f;
+        } else {
+            for (int i = lane; i < FW * PS; i += 32) accw[i] = 0.0f;
+            __syncwarp();
+        }
         // unit rms / crest / peak ride on the sub-segment loads: sub-segment s accounts for its first `step` samples (the rest
         // belongs to its successors), the last one for all of its nperseg samples; samples behind the last sub-segment are
         // swept afterwards.  Every sample of the unit is counted exactly once and read from memory for the FFT only.
@@ -155,11 +172,13 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                     cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
                 }
                 dft_dif_p<R2, 1>(z + q * R2);
-                const int ob = (b - k) * R2 + k;
-                SYG_UNROLL
-                for (int kp = 0; kp < R2; ++kp) zs[zpad<LE>(ob + kp * E)] = z[q * R2 + bitrev(kp, ilog2(R2))];
+                if constexpr (!kShflSplit) {
+                    const int ob = (b - k) * R2 + k;
+                    SYG_UNROLL
+                    for (int kp = 0; kp < R2; ++kp) zs[zpad<LE>(ob + kp * E)] = z[q * R2 + bitrev(kp, ilog2(R2))];
+                }
             }
-            __syncwarp();
+            if constexpr (!kShflSplit) __syncwarp();
             // ---------------- real split -> accumulate |X[k]|^2 ----------------
             {
                 const int jz = (j == 0) ? 1 : 0;
@@ -174,21 +193,48 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                     const int kk = i * G;
                     const int k = j + kk;
                     if (i == E / 2 && j != 0) break;
-                    const float2 zk = zk0[kk + (kk >> LE)];
-                    const int c1 = (M - kk) + ((M - kk - 1) >> LE);
-                    const bool blk = ((M - kk) & (E - 1)) == 0;
-                    float2 zm = blk ? zm1[c1] : zm0[c1];
-                    if (i == 0 && j == 0) zm = zk;
+                    float2 zk, zm;
+                    if constexpr (kShflSplit) {                        // mirrors from the partner lane's registers (mirror_of)
+                        zk = z[zreg_of<E, G>(i)];
+                        zm = zk;                                       // i = E/2 (lane 0): bin M/2 pairs with itself
+                        if (i < E / 2) zm = mirror_of<E, G>(z, i, j);
+                    } else {
+                        zk = zk0[kk + (kk >> LE)];
+                        const int c1 = (M - kk) + ((M - kk - 1) >> LE);
+                        const bool blk = ((M - kk) & (E - 1)) == 0;
+                        zm = blk ? zm1[c1] : zm0[c1];
+                        if (i == 0 && j == 0) zm = zk;
+                    }
                     float2 w = TBLW ? t_tws[k] : __ldg(&t_tws[k]);
                     if (!TBLW) w = make_float2(0.5f * w.x, 0.5f * w.y);
                     float pwk, pwm;
                     split_power(zk, zm, w, pwk, pwm);                  // |X[k]|^2, |X[M-k]|^2 straight from the packed pair (14 instead of 22 operations)
-                    if (valid) {
+                    if constexpr (kRegAcc) {
+                        ak[i] += valid ? pwk : 0.0f;
+                        if (i < E / 2) am[i] += valid ? pwm : 0.0f;
+                    } else if (valid) {
                         pk0[kk + ((kk >> 5) << 2)] += pwk;
                         const int q1 = (M - kk) + (((M - kk - 1) >> 5) << 2);
                         const bool blk5 = ((M - kk) & 31) == 0;
                         if (2 * k != M) (blk5 ? pm1 : pm0)[q1] += pwm;
                     }
+                }
+            }
+            __syncwarp();
+        }
+        if constexpr (kRegAcc) {                                        // every bin of the frame group's accumulator is written exactly once
+            float* const pk0 = acc + j;
+            float* const pm0 = acc - j;
+            float* const pm1 = pm0 + 4 * ((j == 0) ? 1 : 0);
+            SYG_UNROLL
+            for (int i = 0; i <= E / 2; ++i) {
+                const int kk = i * G;
+                if (i == E / 2 && j != 0) break;
+                pk0[kk + ((kk >> 5) << 2)] = ak[i];
+                if (i < E / 2) {
+                    const int q1 = (M - kk) + (((M - kk - 1) >> 5) << 2);
+                    const bool blk5 = ((M - kk) & 31) == 0;
+                    (blk5 ? pm1 : pm0)[q1] = am[i];
                 }
             }
             __syncwarp();
