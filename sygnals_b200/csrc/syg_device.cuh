@@ -122,9 +122,95 @@ SYG_DEVICE SYG_INLINE void rot_w(float2& d, int k) {            // d *= W_R^k
     mul_w<R>(d.x, d.y, k);
 }
 
+// Deferred twiddle scales (SYG_FFT_DEFER, default on).  A rotation by W = c + i s is written c (x - t y, t x + y) with t = s / c
+// (or s (x ct - y, x + y ct) with ct = c / s where |s| > |c|, so |t| <= 1): two FFMA instead of FMUL + FFMA twice, and the factor c
+// is NOT applied -- it stays a compile-time "pending scale" of that element.  The next butterfly absorbs it for free: a + rho b and
+// a - rho b are single FFMA2 whose multiplier is a 32-bit immediate broadcast to both halves (FFMA2 R, R, imm, R), a factor common to
+// both inputs simply carries on, a pending -1 is a sign flip of the constant.  In the radix-2 DIF network every pending scale is
+// absorbed by the last stage (the element with twiddle exponent 0 of each block is never scaled); the tail loop below would apply a
+// left-over one.  All bookkeeping (ps[], the ratios, the branches) is constant-folded after unrolling.  A radix-32 DFT takes
+// 243 instructions instead of 307, a radix-16 one 91 instead of 111.
+#ifndef SYG_FFT_DEFER
+#define SYG_FFT_DEFER 1
+#endif
+SYG_DEVICE SYG_INLINE constexpr double cos32d(int k) {
+    constexpr double c[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                             0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                             0.19509032201612826785, 0.0};
+    k &= 31;
+    if (k > 16) k = 32 - k;
+    return (k <= 8) ? c[k] : -c[16 - k];
+}
+SYG_DEVICE SYG_INLINE constexpr double sin32d(int k) { return cos32d(k - 8); }
+SYG_DEVICE SYG_INLINE constexpr bool scale_same(double a, double b) { return (a - b) < 1e-12 && (b - a) < 1e-12; }
+SYG_DEVICE SYG_INLINE float2 bcast2(double v) { return make_float2((float)v, (float)v); }
+
 template <int R, int S>
 SYG_DEVICE SYG_INLINE void dft_dif_p(float2* z) {
     const float2 neg1 = make_float2(-1.0f, -1.0f);
+#if SYG_FFT_DEFER
+    double ps[R];                                                   // pending scale of every element (compile time after unrolling)
+    SYG_UNROLL
+    for (int i = 0; i < R; ++i) ps[i] = 1.0;
+    SYG_UNROLL
+    for (int half = R / 2; half >= 1; half >>= 1) {
+        SYG_UNROLL
+        for (int base = 0; base < R; base += 2 * half) {
+            SYG_UNROLL
+            for (int k = 0; k < half; ++k) {
+                const int i0 = (base + k) * S, i1 = (base + k + half) * S;
+                const float2 a = z[i0], b = z[i1];
+                const double pa = ps[base + k], pb = ps[base + k + half];
+                const bool same = scale_same(pa, pb), a1 = scale_same(pa, 1.0), b1 = scale_same(pb, 1.0);
+                const int kw = (k * (R / (2 * half))) & (R - 1);
+                const int k32 = kw * (32 / R);
+                // ---- sum: pa a + pb b
+                if (same) { z[i0] = __fadd2_rn(a, b); ps[base + k] = pa; }
+                else if (a1) { z[i0] = __ffma2_rn(b, bcast2(pb), a); ps[base + k] = 1.0; }
+                else if (b1) { z[i0] = __ffma2_rn(a, bcast2(pa), b); ps[base + k] = 1.0; }
+                else { z[i0] = __ffma2_rn(b, bcast2(pb / pa), a); ps[base + k] = pa; }
+                // ---- difference (pa a - pb b) times W_R^kw
+                double pd;
+                if (k32 == 8 || k32 == 24) {                        // * (-i): (d.y, -d.x);  * (+i): (-d.y, d.x) -- the sign goes into the scale
+                    const float rho = same ? 1.0f : (float)(pb / pa);
+                    float2 d;
+                    if (same) d = make_float2(a.y - b.y, b.x - a.x);
+                    else d = make_float2(__fmaf_rn(-rho, b.y, a.y), __fmaf_rn(rho, b.x, -a.x));
+                    z[i1] = d;
+                    pd = (k32 == 8) ? pa : -pa;
+                } else {
+                    float2 d;
+                    if (same) { d = __ffma2_rn(b, neg1, a); pd = pa; }
+                    else if (a1) { d = __ffma2_rn(b, bcast2(-pb), a); pd = 1.0; }
+                    else if (b1) { d = __ffma2_rn(a, bcast2(-pa), b); pd = -1.0; }           // b - pa a = -(pa a - b)
+                    else { d = __ffma2_rn(b, bcast2(-pb / pa), a); pd = pa; }
+                    if (k32 == 16) {
+                        pd = -pd;
+                    } else if (k32 != 0) {
+                        const double c = cos32d(k32), sn = -sin32d(k32);                     // W = c + i sn
+                        const double ac = c < 0.0 ? -c : c, as = sn < 0.0 ? -sn : sn;
+                        const float x = d.x, y = d.y;
+                        if (ac >= as) {                                                      // c ((x - t y) + i (t x + y))
+                            const float t = (float)(sn / c);
+                            d = make_float2(__fmaf_rn(-t, y, x), __fmaf_rn(t, x, y));
+                            pd *= c;
+                        } else {                                                             // sn ((ct x - y) + i (x + ct y))
+                            const float ct = (float)(c / sn);
+                            d = make_float2(__fmaf_rn(ct, x, -y), __fmaf_rn(ct, y, x));
+                            pd *= sn;
+                        }
+                    }
+                    z[i1] = d;
+                }
+                ps[base + k + half] = pd;
+            }
+        }
+    }
+    SYG_UNROLL
+    for (int i = 0; i < R; ++i) {
+        if (!scale_same(ps[i], 1.0)) z[i * S] = __fmul2_rn(z[i * S], bcast2(ps[i]));
+    }
+#else
     SYG_UNROLL
     for (int half = R / 2; half >= 1; half >>= 1) {
         SYG_UNROLL
@@ -150,6 +236,7 @@ SYG_DEVICE SYG_INLINE void dft_dif_p(float2* z) {
             }
         }
     }
+#endif
 }
 
 // complex multiply by a run-time twiddle (wr + i wi)

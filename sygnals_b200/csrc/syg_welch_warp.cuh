@@ -25,7 +25,10 @@ struct WelchWarpTile {
     static constexpr int FW = WT::FW, ZS = WT::ZS;
     // accumulator pitch: the FW lane groups of a warp add to their own accumulators in the same 32-bit shared-memory access, so the
     // groups (G = 32 / FW lanes each) must start G banks apart: pitch = G (mod 32), at least WarpTile::PS
-    static constexpr int PS = (FW == 1 || TBLW) ? WT::PS : ((WT::PS - WT::G + 31) / 32 * 32 + WT::G);
+    // (WarpTile::PS carries 48 words of slack for the mel sweep of the feature kernel: not needed here, which is what lets the
+    // padded pitch fit the 16-warp CTA of the TBLW instantiation)
+    static constexpr int PS0 = TBLW ? ((WT::M + 1) + 4 * ((WT::M + 1) >> 5) + 3) / 4 * 4 : WT::PS;
+    static constexpr int PS = (FW == 1) ? PS0 : ((PS0 - WT::G + 31) / 32 * 32 + WT::G);
     static constexpr int ZR = (2 * ZS + 3) / 4 * 4;                  // floats of one Z region
     static constexpr int warp_floats = FW * (ZR + PS);               // Z regions, then the accumulators
     static constexpr size_t table_bytes = TBLW ? (size_t)(2 * WT::M * 4 + WT::M * 8 + (WT::M / 2 + 1) * 8) : 0;
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
     if (TBLW) {
         for (int i = tid; i < M; i += NT) {
             tbw[i] = __ldg(reinterpret_cast<const float2*>(a.window) + i);
-            tbw[M + i] = __ldg(a.tw + i);
+            tbw[M + i] = __ldg(a.tw + (i / E) * (i % E));                // transposed for pass 2: entry [r][k] = W_M^{r k} (as frame_warp_kernel)
         }
         for (int i = tid; i <= M / 2; i += NT) {                        // split twiddles with the halving folded in (split_power)
             const float2 w = __ldg(a.tws + i);
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                 const int k = b & (E - 1);
                 SYG_UNROLL
                 for (int r = 1; r < R2; ++r) {
-                    const float2 w = TBLW ? t_tw[r * k] : __ldg(&t_tw[r * k]);
+                    const float2 w = TBLW ? t_tw[r * E + k] : __ldg(&t_tw[r * k]);
                     cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
                 }
                 dft_dif_p<R2, 1>(z + q * R2);
