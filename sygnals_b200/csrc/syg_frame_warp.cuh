@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     constexpr int B = M + 1;
     static_assert(R2 == G, "two-pass warp tile: the last radix equals the lanes per frame");
     constexpr bool kShflSplit = (SYG_SPLIT_SHFL != 0);                  // mirrors of the real split by SHFL (syg_device.cuh: mirror_of)
+    // feature stages: pass 2 produces Z/2 (halved twiddle table, element 0 entering with the pending scale 0.5) and the split runs in tangent form (split_power_h)
+    constexpr bool kHalfZ = (STAGE == 0 || STAGE == 5) && (SYG_SPLIT_HALF != 0);
     SYG_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -180,9 +182,15 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         float2* d_tw = const_cast<float2*>(t_tw);
         // transposed for the pass-2 access: entry [r][k] = W_M^{r k} (r < R2, k < E; R2 E = M), so that the lanes of a warp
         // (consecutive k) read consecutive words instead of stride-r ones
-        for (int i = tid; i < M; i += NT) d_tw[i] = __ldg(a.tw + (i / E) * (i % E));
+        for (int i = tid; i < M; i += NT) {
+            const float2 w = __ldg(a.tw + (i / E) * (i % E));
+            d_tw[i] = kHalfZ ? make_float2(0.5f * w.x, 0.5f * w.y) : w;
+        }
         float2* d_twsh = const_cast<float2*>(t_twsh);
-        for (int i = tid; i <= M / 2; i += NT) d_twsh[i] = __ldg((STAGE == 4 ? a.tws : a.twsh) + i);
+        for (int i = tid; i <= M / 2; i += NT) {
+            if (kHalfZ) d_twsh[i] = split_twiddle_h(__ldg(a.tws + i), 4 * i < M);
+            else d_twsh[i] = __ldg((STAGE == 4 ? a.tws : a.twsh) + i);
+        }
         if ((STAGE == 0 || STAGE == 5) && (a.mask & syg::FB_MFCC)) {
             int4* d_sl = const_cast<int4*>(t_slots);
             for (int i = tid; i < a.n_mels; i += NT) d_sl[i] = __ldg(a.mel_slots + i);
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         // ---------------- framing + window + time-domain partial statistics ----------------
         float2 z[E];
         float2 sq2 = make_float2(0.0f, 0.0f);
-        float pk = 0.0f, pk2 = 0.0f;
+        float pk = 0.0f;
         double s_sum = 0.0, s_abs = 0.0, s_sqd = 0.0;
         {
             const float* src = a.y + ur.start + p0;
@@ -266,8 +274,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     const float2 v = __ldg(reinterpret_cast<const float2*>(src) + c);
                     const float2 w = TBL ? w2[c] : __ldg(w2 + c);
                     sq2 = __ffma2_rn(v, v, sq2);
-                    pk = fmaxf(pk, fabsf(v.x));
-                    pk2 = fmaxf(pk2, fabsf(v.y));
+                    pk = fmaxf(fmaxf(pk, fabsf(v.x)), fabsf(v.y));         // one FMNMX3 (|.| are operand modifiers)
                     if (EXTRA) {
                         s_sum += (double)v.x + (double)v.y;
                         s_abs += (double)fabsf(v.x) + (double)fabsf(v.y);
@@ -302,8 +309,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     }
                     const float2 w = TBL ? w2[c] : __ldg(w2 + c);
                     sq2 = __ffma2_rn(v, v, sq2);
-                    pk = fmaxf(pk, fabsf(v.x));
-                    pk2 = fmaxf(pk2, fabsf(v.y));
+                    pk = fmaxf(fmaxf(pk, fabsf(v.x)), fabsf(v.y));         // one FMNMX3 (|.| are operand modifiers)
                     if (EXTRA) {
                         s_sum += (double)v.x + (double)v.y;
                         s_abs += (double)fabsf(v.x) + (double)fabsf(v.y);
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 const float2 w = TBL ? t_tw[r * E + k] : __ldg(&t_tw[(r * k) << SH]);
                 cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
             }
-            dft_dif_p<R2, 1>(z + q * R2);
+            dft_dif_p<R2, 1, kHalfZ>(z + q * R2);
             if constexpr (!kShflSplit) {
                 const int ob = (b - k) * R2 + k;
                 SYG_UNROLL
@@ -420,7 +426,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 }
                 const float2 wh = TBL ? t_twsh[k] : __ldg(&t_twsh[k]);
                 float pwk, pwm;
-                split_power(zk[i], zm[i], wh, pwk, pwm);
+                if constexpr (kHalfZ) split_power_h(4 * i < E, zk[i], zm[i], wh, pwk, pwm);   // k = j + G i < M/4 for every lane iff i < E/4
+                else split_power(zk[i], zm[i], wh, pwk, pwm);
                 pk0[kk + ((kk >> 5) << 2)] = pwk;
                 const int q1 = (M - kk) + (((M - kk - 1) >> 5) << 2);
                 const bool blk = ((M - kk) & 31) == 0;
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         // ---------------- time-domain features (unwindowed, zero-padded frame) ----------------
         if (a.mask & syg::FB_TIME_ANY) {
             const float tsq = lanes_sum<G>(sq2.x + sq2.y);
-            const float tpk = lanes_max<G>(fmaxf(pk, pk2));
+            const float tpk = lanes_max<G>(pk);
             if (j == 0 && valid) {
                 const float rms = sqrt_approx(tsq * (1.0f / (float)TL::NFFT));     // MUFU.SQRT (1 ulp) instead of the IEEE sequence; bar: rel 1e-5
                 if (a.row_rms >= 0) orow[(long long)a.row_rms * a.T] = rms;
@@ -512,23 +519,29 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     p[4 * i] = v.x; p[4 * i + 1] = v.y; p[4 * i + 2] = v.z; p[4 * i + 3] = v.w;
                 }
             }
-            float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sm[2] = {0.0f, 0.0f}, skm[2] = {0.0f, 0.0f};
+            // bin pairs (i, i + 1) in FP32x2: power sums (two packed accumulators), magnitude sums and sum i * mag with the EVEN index
+            // as the broadcast multiplier of both halves -- the odd bins' missing "+ 1" is the packed magnitude sum's odd half
+            float2 sp2[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+            float2 sm2 = make_float2(0.0f, 0.0f), skm2 = make_float2(0.0f, 0.0f);
             float slog = 0.0f, vmax = -1.0f;
             int imax = 0;
             SYG_UNROLL
-            for (int i = 0; i < E; ++i) {
-                const float mg = sqrt_approx(p[i]);
-                sp[i & 3] += p[i];
-                sm[i & 1] += mg;
-                skm[i & 1] = __fmaf_rn(mg, (float)i, skm[i & 1]);
+            for (int i = 0; i < E; i += 2) {
+                const float2 mg2 = make_float2(sqrt_approx(p[i]), sqrt_approx(p[i + 1]));
+                sp2[(i >> 1) & 1] = __fadd2_rn(sp2[(i >> 1) & 1], make_float2(p[i], p[i + 1]));
+                sm2 = __fadd2_rn(sm2, mg2);
+                skm2 = __ffma2_rn(mg2, make_float2((float)i, (float)i), skm2);
                 if (EXTRA) {
-                    if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p[i]) + 2.220446049250313e-16f);
-                    if (p[i] > vmax) { vmax = p[i]; imax = k0 + i; }
+                    SYG_UNROLL
+                    for (int h = 0; h < 2; ++h) {
+                        if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p[i + h]) + 2.220446049250313e-16f);
+                        if (p[i + h] > vmax) { vmax = p[i + h]; imax = k0 + i + h; }
+                    }
                 }
             }
-            float lsp = (sp[0] + sp[1]) + (sp[2] + sp[3]);
-            float lsm = sm[0] + sm[1];
-            float lskm = __fmaf_rn(lsm, (float)k0, skm[0] + skm[1]);     // sum (k0 + i) mag_i
+            float lsp = (sp2[0].x + sp2[0].y) + (sp2[1].x + sp2[1].y);
+            float lsm = sm2.x + sm2.y;
+            float lskm = __fmaf_rn(lsm, (float)k0, (skm2.x + skm2.y) + sm2.y);     // sum (k0 + i) mag_i
             const float p_ny = pf[ppad(M)];
             if (j == G - 1) {                                            // bin M (Nyquist)
                 const float mg = sqrt_approx(p_ny);

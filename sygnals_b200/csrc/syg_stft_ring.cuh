@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
     constexpr int Q = E / R2, B = M + 1, NT = RG::NT, TT = RG::TT, TTP = RG::TTP, RSS = RG::RSR, WF = RG::WF;
     static_assert(R2 == G, "two-pass warp tile");
     constexpr bool kShflSplit = (SYG_SPLIT_SHFL != 0);                  // mirrors of the real split by SHFL (syg_device.cuh: mirror_of)
+    constexpr bool kHalfZ = (SYG_SPLIT_HALF != 0);
     SYG_DYN_SMEM(smem_raw);
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem_raw);          // [S] "stage full"
     float* const fb = reinterpret_cast<float*>(smem_raw + RG::kBarBytes);
@@ -74,10 +75,14 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
     float2* const zs = reinterpret_cast<float2*>(wbase + f * RSS);
 
     for (int i = tid; i < M; i += NT) t_win[i] = __ldg(reinterpret_cast<const float2*>(a.window) + i);
-    for (int i = tid; i < M; i += NT) t_tw[i] = __ldg(a.tw + (i / E) * (i % E));
+    // kHalfZ: pass 2 produces Z/2 (halved twiddles, element 0 entering with the pending scale 0.5), split in tangent form (split_power_h)
+    for (int i = tid; i < M; i += NT) {
+        const float2 w = __ldg(a.tw + (i / E) * (i % E));
+        t_tw[i] = kHalfZ ? make_float2(0.5f * w.x, 0.5f * w.y) : w;
+    }
     for (int i = tid; i <= M / 2; i += NT) {
         const float2 w = __ldg(a.tws + i);
-        t_twsh[i] = make_float2(0.5f * w.x, 0.5f * w.y);
+        t_twsh[i] = kHalfZ ? split_twiddle_h(w, 4 * i < M) : make_float2(0.5f * w.x, 0.5f * w.y);
     }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
                 const float2 w = t_tw[r * E + k];
                 cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
             }
-            dft_dif_p<R2, 1>(z + q * R2);
+            dft_dif_p<R2, 1, kHalfZ>(z + q * R2);
             if constexpr (!kShflSplit) {
                 const int ob = (b - k) * R2 + k;
                 SYG_UNROLL
@@ -223,7 +228,8 @@ __global__ void __launch_bounds__(NW * 32, 1) stft_ring_kernel(const syg::FrameA
                     if (ii == 0 && j == 0) zm = zk;                                            // k = 0 pairs with itself (DC / Nyquist)
                 }
                 float pk_, pm_;
-                split_power(zk, zm, t_twsh[k], pk_, pm_);
+                if constexpr (kHalfZ) split_power_h(4 * ii < E, zk, zm, t_twsh[k], pk_, pm_);
+                else split_power(zk, zm, t_twsh[k], pk_, pm_);
                 if (a.out_kind == 1) { pk_ = sqrt_approx(pk_); pm_ = sqrt_approx(pm_); }
                 tcol[k * TTP] = pk_;
                 if (2 * k != M) tcol[(M - k) * TTP] = pm_;

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
     constexpr int Q = E / R2;
     static_assert(R2 == G, "two-pass warp tile");
     constexpr bool kShflSplit = (SYG_SPLIT_SHFL != 0);                  // mirrors of the real split by SHFL (syg_device.cuh: mirror_of)
+    constexpr bool kHalfZ = TBLW && (SYG_SPLIT_HALF != 0);              // tables in shared memory: Z/2 from pass 2 + split_power_h
 #ifndef SYG_WELCH_REGACC
 #define SYG_WELCH_REGACC 0
 #endif
@@ -66,11 +67,12 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
     if (TBLW) {
         for (int i = tid; i < M; i += NT) {
             tbw[i] = __ldg(reinterpret_cast<const float2*>(a.window) + i);
-            tbw[M + i] = __ldg(a.tw + (i / E) * (i % E));                // transposed for pass 2: entry [r][k] = W_M^{r k} (as frame_warp_kernel)
+            const float2 w = __ldg(a.tw + (i / E) * (i % E));            // transposed for pass 2: entry [r][k] = W_M^{r k} (as frame_warp_kernel)
+            tbw[M + i] = kHalfZ ? make_float2(0.5f * w.x, 0.5f * w.y) : w;
         }
-        for (int i = tid; i <= M / 2; i += NT) {                        // split twiddles with the halving folded in (split_power)
+        for (int i = tid; i <= M / 2; i += NT) {                        // split twiddles: tangent form (split_power_h) or with the halving folded in (split_power)
             const float2 w = __ldg(a.tws + i);
-            tbw[2 * M + i] = make_float2(0.5f * w.x, 0.5f * w.y);
+            tbw[2 * M + i] = kHalfZ ? split_twiddle_h(w, 4 * i < M) : make_float2(0.5f * w.x, 0.5f * w.y);
         }
         __syncthreads();
     }
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                     const float2 w = TBLW ? t_tw[r * E + k] : __ldg(&t_tw[r * k]);
                     cmul(z[q * R2 + r].x, z[q * R2 + r].y, w.x, w.y);
                 }
-                dft_dif_p<R2, 1>(z + q * R2);
+                dft_dif_p<R2, 1, kHalfZ>(z + q * R2);
                 if constexpr (!kShflSplit) {
                     const int ob = (b - k) * R2 + k;
                     SYG_UNROLL
@@ -211,7 +213,8 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                     float2 w = TBLW ? t_tws[k] : __ldg(&t_tws[k]);
                     if (!TBLW) w = make_float2(0.5f * w.x, 0.5f * w.y);
                     float pwk, pwm;
-                    split_power(zk, zm, w, pwk, pwm);                  // |X[k]|^2, |X[M-k]|^2 straight from the packed pair (14 instead of 22 operations)
+                    if constexpr (kHalfZ) split_power_h(4 * i < E, zk, zm, w, pwk, pwm);
+                    else split_power(zk, zm, w, pwk, pwm);             // |X[k]|^2, |X[M-k]|^2 straight from the packed pair (14 instead of 22 operations)
                     if constexpr (kRegAcc) {
                         ak[i] += valid ? pwk : 0.0f;
                         if (i < E / 2) am[i] += valid ? pwm : 0.0f;
