@@ -625,7 +625,7 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
         static int fin_tt = -1;                                       // SYGB200_FIN_TT=32|64 overrides the tile height (A/B)
         if (fin_tt < 0) { const char* e = std::getenv("SYGB200_FIN_TT"); fin_tt = e ? std::atoi(e) : 0; }
         const int tt = fin_tt == 32 || fin_tt == 64 ? fin_tt : ((f.row_mfcc >= 0 && f.n_mels <= 64) ? 64 : 32);
-        const size_t smem = (size_t)tt * sygdev::fin_pitch(f.n_mels) * sizeof(float);     // FP32 S_db tile
+        const size_t smem = sygdev::fin_smem_bytes(tt, f.n_mels, f.dct_fold != 0);         // folded FP64 S_db rows
         const long long n_tiles = (g.n_units * (long long)pl.T + tt - 1) / tt;
         static int fin_cap = -1;                                      // SYGB200_FIN_CTAS: CTAs per SM of the finalize grid (0 = one CTA per tile)
         if (fin_cap < 0) { const char* e = std::getenv("SYGB200_FIN_CTAS"); fin_cap = e ? std::atoi(e) : 0; }

@@ -29,8 +29,13 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel_t(const syg::Finaliz
     const int N = a.n_mels;
     const int H = a.dct_fold ? (N + 1) / 2 : N;
     const int H4 = (H + 3) / 4 * 4;                                     // DMMA k-steps of 4 columns
-    const int P = fin_pitch(N);
-    float* const xs = reinterpret_cast<float*>(smem_raw);              // [kFinTT][P] S_db (FP32, as the reference's float32->float64 values)
+    // FP64 rows in shared memory, folded on the way in: xe[tt][k] = s[k] + s[N-1-k] (what the even DCT-II coefficients see),
+    // xo[tt][k] = s[k] - s[N-1-k] (odd coefficients), k < H = ceil(N/2); other DCT types keep the unfolded row in xe (H = N).
+    // The DMMA loop then is one table load, one shared-memory load and one mma per k-step: the float -> double conversions, the
+    // fold and their predicates used to sit INSIDE that loop (~45 instructions per k-step; the kernel was issue-bound at 82 %).
+    const int PD = fin_pitch_d(H);
+    double* const xe = reinterpret_cast<double*>(smem_raw);            // [kFinTT][PD]
+    double* const xo = xe + (a.dct_fold ? kFinTT * PD : 0);            // [kFinTT][PD] (folded types only)
     const int warp = tid >> 5, lane = tid & 31;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -51,82 +56,78 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel_t(const syg::Finaliz
         }
         __syncthreads();
         if (a.row_mfcc >= 0) {
-            // S_db tile: the chunk's raw mel energies of these frames are ONE contiguous block of nt * N floats -> coalesced 16-byte
-            // loads, four in flight per thread before the first use (the kernel is bound by the latency of these loads), dB
-            // conversion with the frame's reference / clamp, FP32 tile in shared memory.
-            {
-                const float* const blk = a.melws + gf0 * N;             // 128 N bytes per full tile: 16-byte aligned
-                const int n_el = nt * N, n_ch = (n_el + 3) >> 2;
-                for (int c0 = tid; c0 < n_ch; c0 += 4 * kThreads) {
-                    float4 v[4];
-                    SYG_UNROLL
-                    for (int r = 0; r < 4; ++r) {
-                        const int c = c0 + r * kThreads, e = 4 * c;
-                        v[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        if (e + 3 < n_el) v[r] = __ldg(reinterpret_cast<const float4*>(blk) + c);
-                        else if (e < n_el) {
-                            v[r].x = __ldg(blk + e);
-                            if (e + 1 < n_el) v[r].y = __ldg(blk + e + 1);
-                            if (e + 2 < n_el) v[r].z = __ldg(blk + e + 2);
+            const float* const blk = a.melws + gf0 * N;                 // the tile's raw mel energies: ONE contiguous block of nt * N floats
+            if (a.dct_fold && (N & 7) == 0) {
+                // fast path (N a multiple of 8: H a multiple of 4, every float4 inside one row, 16-byte aligned): a thread takes the
+                // chunk k..k+3 of a row and its mirror N-4-k..N-1-k (the CTAs of an SM hide each other's load latency)
+                const int cpr = H >> 2;                                 // chunk pairs per row
+                const int n_cp = nt * cpr;
+                for (int c = tid; c < n_cp; c += kThreads) {
+                    const int tt = c / cpr, k = (c - tt * cpr) << 2;
+                    const float* row = blk + (size_t)tt * N;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(row + k));
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(row + N - 4 - k));
+                    const float ref_db = s_ref[tt], floor_db = s_floor[tt];
+                    const float x0 = fmaxf(db10(fmaxf(a.amin, v.x)) - ref_db, floor_db), y0 = fmaxf(db10(fmaxf(a.amin, m.w)) - ref_db, floor_db);
+                    const float x1 = fmaxf(db10(fmaxf(a.amin, v.y)) - ref_db, floor_db), y1 = fmaxf(db10(fmaxf(a.amin, m.z)) - ref_db, floor_db);
+                    const float x2 = fmaxf(db10(fmaxf(a.amin, v.z)) - ref_db, floor_db), y2 = fmaxf(db10(fmaxf(a.amin, m.y)) - ref_db, floor_db);
+                    const float x3 = fmaxf(db10(fmaxf(a.amin, v.w)) - ref_db, floor_db), y3 = fmaxf(db10(fmaxf(a.amin, m.x)) - ref_db, floor_db);
+                    double2* const pe = reinterpret_cast<double2*>(xe + tt * PD + k);
+                    double2* const po = reinterpret_cast<double2*>(xo + tt * PD + k);
+                    pe[0] = make_double2((double)x0 + (double)y0, (double)x1 + (double)y1);
+                    pe[1] = make_double2((double)x2 + (double)y2, (double)x3 + (double)y3);
+                    po[0] = make_double2((double)x0 - (double)y0, (double)x1 - (double)y1);
+                    po[1] = make_double2((double)x2 - (double)y2, (double)x3 - (double)y3);
+                }
+            } else {
+                // any N, any DCT type: one (frame, column) per thread and step; columns H..PD-1 are zero (the k-steps run to H4)
+                const int n_el = nt * PD;
+                for (int i = tid; i < n_el; i += kThreads) {
+                    const int tt = i / PD, k = i - tt * PD;
+                    double e = 0.0, o = 0.0;
+                    if (k < H) {
+                        const float* row = blk + (size_t)tt * N;
+                        const float ref_db = s_ref[tt], floor_db = s_floor[tt];
+                        const float x = fmaxf(db10(fmaxf(a.amin, __ldg(row + k))) - ref_db, floor_db);
+                        e = (double)x;
+                        if (a.dct_fold) {
+                            const int k2 = N - 1 - k;
+                            if (k2 != k) {
+                                const float y = fmaxf(db10(fmaxf(a.amin, __ldg(row + k2))) - ref_db, floor_db);
+                                e = (double)x + (double)y;
+                                o = (double)x - (double)y;
+                            }                                           // centre of an odd N: once, even coefficients only
                         }
                     }
-                    SYG_UNROLL
-                    for (int r = 0; r < 4; ++r) {
-                        const int e = 4 * (c0 + r * kThreads);
-                        if (e >= n_el) break;
-                        int tt = e / N, n = e - tt * N;
-                        const float in[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
-                        if (n + 3 < N && e + 3 < n_el) {                // chunk inside one row (always, when N is a multiple of 4)
-                            const float ref_db = s_ref[tt], floor_db = s_floor[tt];
-                            float4 o;
-                            o.x = fmaxf(db10(fmaxf(a.amin, in[0])) - ref_db, floor_db);
-                            o.y = fmaxf(db10(fmaxf(a.amin, in[1])) - ref_db, floor_db);
-                            o.z = fmaxf(db10(fmaxf(a.amin, in[2])) - ref_db, floor_db);
-                            o.w = fmaxf(db10(fmaxf(a.amin, in[3])) - ref_db, floor_db);
-                            if ((n & 3) == 0) *reinterpret_cast<float4*>(xs + tt * P + n) = o;
-                            else { xs[tt * P + n] = o.x; xs[tt * P + n + 1] = o.y; xs[tt * P + n + 2] = o.z; xs[tt * P + n + 3] = o.w; }
-                        } else {
-                            for (int q = 0; q < 4 && e + q < n_el; ++q) {
-                                xs[tt * P + n] = fmaxf(db10(fmaxf(a.amin, in[q])) - s_ref[tt], s_floor[tt]);
-                                if (++n == N) { n = 0; ++tt; }
-                            }
-                        }
-                    }
+                    xe[i] = e;
+                    if (a.dct_fold) xo[i] = o;
                 }
             }
             __syncthreads();
             // DCT as FP64 tensor-core products (mma.sync m8n8k4, DMMA): D[coefficient][frame] += dct[coefficient][n] * S[frame][n].
-            // Warp w owns one parity (even coefficients see the folded sums, odd ones the differences: see the B fragment below) and one
-            // n-tile of 8 frames; 8 coefficients of that parity per m-tile.  Per k-step of 4 mel columns a lane loads ONE table
-            // entry and ONE tile entry for 256 multiply-adds of the warp (the scalar version needed 1.5 loads per FMA and was
-            // bound by the load/store unit: 3.5 ms per 10 h of audio).
+            // Warp w owns one parity (even coefficients see the folded sums, odd ones the differences) and one n-tile of 8 frames;
+            // 8 coefficients of that parity per m-tile.  Per k-step of 4 columns a lane loads ONE table entry and ONE tile entry for
+            // 256 multiply-adds of the warp.  Rows of a partial tile beyond nt hold stale values: a B column only feeds its own
+            // (unstored) output column.
             {
                 const int par = warp & 1;                               // kThreads / 32 = 8 warps: 2 parities x 4 n-tiles of 8 frames (per 32 frames)
                 const int g = lane >> 2, q = lane & 3;
                 const int n_par = par ? a.n_mfcc / 2 : (a.n_mfcc + 1) / 2;
-                const double sgn = par ? -1.0 : 1.0;
+                const double* const xp = (par && a.dct_fold) ? xo : xe;
                 for (int nt8 = (warp >> 1) * 8; nt8 < kFinTT; nt8 += 32)
                 for (int m0 = 0; m0 < n_par; m0 += 8) {
-                    const float* const xrow = xs + (nt8 + g) * P;        // this lane's frame (B column)
+                    const double* const xrow = xp + (nt8 + g) * PD + q;  // this lane's frame (B column)
                     const int c_a = par + 2 * (m0 + g);                 // coefficient of this lane's A row
                     const bool a_ok = c_a < a.n_mfcc;
                     const double* const drow = a.dct + (long long)(a_ok ? c_a : 0) * N + q;
+                    const int kmax = a_ok ? H - q : 0;                  // table entries of this lane: k0 < kmax
                     double d0 = 0.0, d1 = 0.0;
+#ifndef SYG_EMU
+#pragma unroll 4
+#endif
                     for (int k0 = 0; k0 < H4; k0 += 4) {
-                        const int k = k0 + q;
-                        const double av = (a_ok && k < H) ? __ldg(drow + k0) : 0.0;
-                        // DCT-II rows are (-1)^c symmetric about the centre (cos(pi c (2(N-1-n)+1) / 2N) = (-1)^c cos(pi c (2n+1) / 2N)):
-                        // even coefficients see s[n] + s[N-1-n], odd ones s[n] - s[N-1-n], n < ceil(N/2) (centre of an odd N once);
-                        // folded here, in FP64, on the way into the fragment.  Other DCT types read the unfolded row.
-                        double bv = 0.0;
-                        if (k < H) {
-                            bv = (double)xrow[k];
-                            if (a.dct_fold) {
-                                const int k2 = N - 1 - k;
-                                bv = (k2 != k) ? bv + sgn * (double)xrow[k2] : (par ? 0.0 : bv);
-                            }
-                        }
-                        mma_m8n8k4_f64(d0, d1, av, bv);
+                        const double av = (k0 < kmax) ? __ldg(drow + k0) : 0.0;
+                        mma_m8n8k4_f64(d0, d1, av, xrow[k0]);
                     }
                     // lane holds D[row g][cols 2q, 2q+1] = coefficient par + 2 (m0 + g) of frames nt8 + 2q, nt8 + 2q + 1
                     if (a_ok) {

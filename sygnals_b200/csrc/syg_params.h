@@ -14,6 +14,16 @@ constexpr int kFinTT = 32;                  // frames per finalize CTA
 __host__ __device__
 #endif
 inline int fin_pitch(int N) { int p = (N + 3) / 4 * 4; while ((p & 7) != 4) p += 4; return p; }
+// finalize_kernel: pitch (in doubles) of the folded FP64 rows in shared memory, H = columns of a row.  A multiple of 4 (the DMMA
+// k-step) and = 4 (mod 16): the B-fragment read of a half-warp -- 4 frames x 4 consecutive doubles -- then covers 32 distinct banks.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int fin_pitch_d(int H) { int p = (H + 3) / 4 * 4; while ((p & 15) != 4) p += 4; return p; }
+inline size_t fin_smem_bytes(int tt, int n_mels, bool fold) {
+    const int H = fold ? (n_mels + 1) / 2 : n_mels;
+    return (size_t)(fold ? 2 : 1) * tt * fin_pitch_d(H) * sizeof(double);
+}
 
 // shared-memory layout (float words) of the mixed-radix kernels for L complex points, B bins and nt threads per CTA
 struct MixedLayout {
