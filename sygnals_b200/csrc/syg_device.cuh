@@ -600,6 +600,18 @@ SYG_DEVICE SYG_INLINE float warp_extreme_mean_sqrt(const float* p, int lo, int c
 }
 
 // --------------------------------------------------------------------------------------------------------
+// fire-and-forget maximum on a global word.  atomicMax() called by a single lane still goes through the compiler's warp
+// aggregation (VOTE + REDUX + leader election: 7 instructions for one active lane); `red` is the one instruction that is needed.
+// --------------------------------------------------------------------------------------------------------
+SYG_DEVICE SYG_INLINE void red_max_u32(unsigned* p, unsigned v) {
+#if defined(SYG_EMU)
+    atomicMax(p, v);
+#else
+    asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+
+// --------------------------------------------------------------------------------------------------------
 // hardware square root (flush-to-zero: a denormal |X|^2 is silence)
 // --------------------------------------------------------------------------------------------------------
 SYG_DEVICE SYG_INLINE float sqrt_approx(float x) {
@@ -785,6 +797,11 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
         // scheduler to interleave.  Pops are selects, not branches.
         // (bulk rounds -- pop every head above the warp maximum of the second keys at once, ~7 per round -- were measured in
         // round 1: two more REDUX per round cost more than the saved rounds, +1.3 % kernel time.  Rejected.)
+        // The 4th key needs a refill (the bare lane tag: smaller than every real key) only where a lane may pop MORE than its four
+        // tracked keys' worth: n > 4 pops from lanes that own at most four elements.  With n <= 4 at most four pops come from one
+        // lane (the stale copies of the 4th key that the shifts leave behind are never reached), and under the T criterion above
+        // every popped key is > T >= each lane's 4th key, so a 4th key never pops at all.  Saves two selects per popped pair.
+        const bool refill = n > 4 && ((count + 31) >> 5) <= 4;
         SYG_UNROLL_BY(UP)
         for (int it = 0; it < n; ++it) {
             const unsigned ga = __reduce_max_sync(kFull, a0);
@@ -792,8 +809,9 @@ SYG_DEVICE SYG_INLINE float2 band_peak_valley_stream(const float* __restrict__ p
             const bool oa = (a0 == ga), ob = (b0 == gb);
             sa += sqrt_approx(__uint_as_float(ga));
             sb += sqrt_approx(__uint_as_float(~gb));
-            a0 = oa ? a1 : a0; a1 = oa ? a2 : a1; a2 = oa ? a3 : a2; a3 = oa ? tag : a3;
-            b0 = ob ? b1 : b0; b1 = ob ? b2 : b1; b2 = ob ? b3 : b2; b3 = ob ? tag : b3;
+            a0 = oa ? a1 : a0; a1 = oa ? a2 : a1; a2 = oa ? a3 : a2;
+            b0 = ob ? b1 : b0; b1 = ob ? b2 : b1; b2 = ob ? b3 : b2;
+            if (refill) { a3 = oa ? tag : a3; b3 = ob ? tag : b3; }
         }
     } else {
         int ha = min(mine, 4), hb = ha;                         // tracked keys left

@@ -676,12 +676,9 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     vmx = fmaxf(vmx, pv.y);
                 }
                 if (lane < 2 * a.nb) a.cws[gff * (2 * a.nb) + lane] = mine_pv;   // one coalesced store per frame (nb <= kMaxBands = 12)
-                const long long uff = __shfl_sync(kFull, u, ff * G);    // unit of frame ff (all lanes take part)
-                if (lane == 0) {
-                    unsigned* um = a.unit_max + uff * 4;
-                    if (pmx > 0.0f) atomicMax(&um[1], __float_as_uint(pmx));
-                    if (vmx > 0.0f) atomicMax(&um[2], __float_as_uint(vmx));
-                }
+                const long long uff = (FW == 1) ? u : __shfl_sync(kFull, u, ff * G);   // unit of frame ff (FW == 1: warp uniform already)
+                const float mx12 = lane ? vmx : pmx;                    // lane 0: peaks -> word 1, lane 1: valleys -> word 2
+                if (lane < 2 && mx12 > 0.0f) red_max_u32(a.unit_max + uff * 4 + 1 + lane, __float_as_uint(mx12));
             }
         }
         __syncwarp();                                                   // interval-form mel overwrites the spectrum: contrast has read it
@@ -822,10 +819,10 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 }
             }
             const float gmx = lanes_max<GS>(fmaxf(fmx, 0.0f));
-            const long long umf = __shfl_sync(kFull, u, mf * G);       // unit of frame mf (all lanes take part)
+            const long long umf = (FW == 1) ? u : __shfl_sync(kFull, u, mf * G);   // unit of frame mf (all lanes take part)
             if (sl == 0 && fvalid && gmx > 0.0f) {
                 if (RES) atomicMax(&res_umax[(int)(umf - grp_u0)], __float_as_uint(gmx));
-                else atomicMax(&a.unit_max[umf * 4 + 0], __float_as_uint(gmx));
+                else red_max_u32(a.unit_max + umf * 4, __float_as_uint(gmx));
             }
         }
 
