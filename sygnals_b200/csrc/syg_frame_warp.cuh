@@ -241,9 +241,13 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         // (measured in round 2: re-aligning the warps of one scheduler with a named barrier once per frame, so that they share
         // instruction fetches of the ~50 KB loop body, costs +2.4 % -- the phase diversity is worth more than the fetches)
         const long long gf = gf_run;
-        const bool valid = gf < frame_end;
-        const long long u = valid ? u_run : 0;
-        const int t = valid ? t_run : 0;
+        // one frame per warp and no barrier inside the task (feature stage): a task past the end is simply skipped, and `valid` is a
+        // compile-time true for everything below (no predicates on the feature stores, no branches around the workspace rows)
+        constexpr bool kSkipInvalid = (STAGE == 0 && FW == 1);
+        const bool valid_rt = gf < frame_end;
+        const bool valid = kSkipInvalid ? true : valid_rt;
+        const long long u = (kSkipInvalid || valid) ? u_run : 0;
+        const int t = (kSkipInvalid || valid) ? t_run : 0;
         if (STAGE == 4 && ((task0 + 1) & (SUBS - 1)) != 0) {          // next task of the same super task: FW frames on
             gf_run += FW;
             t_run += FW;
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             t_run += dt;
         }
         while (t_run >= a.T) { t_run -= a.T; ++u_run; }
+        if (kSkipInvalid && !valid_rt) continue;
         UnitRef ur = unit_ref(a.g, u);
         if (!valid) ur.valid = 0;
         const long long p0 = (long long)t * a.hop - a.cpad;
@@ -651,7 +656,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         if (a.mask & syg::FB_CONTRAST) {
             for (int ff = 0; ff < FW; ++ff) {
                 const long long gff = tf0 + ff;
-                if (gff >= frame_end) break;
+                if (!kSkipInvalid && gff >= frame_end) break;
                 const float* pp = pww + ff * RSS;
                 float pmx = 0.0f, vmx = 0.0f;
                 float mine_pv = 0.0f;                                   // lane bd keeps band bd's peak, lane nb + bd its valley
@@ -689,7 +694,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             constexpr int GS = 32 / FW;
             const int mf = lane / GS, sl = lane % GS;                   // frame of the warp task, slot within the sweep group
             const long long gmf = tf0 + mf;
-            const bool fvalid = gmf < frame_end;
+            const bool fvalid = kSkipInvalid ? true : (gmf < frame_end);
             // STAGE 5: the energies stay in the CTA tile (row = frame within the group)
             float* const mrow = RES ? res_tile + (size_t)(gmf - grp_f0) * res_P : a.melws + gmf * a.n_mels;
             const float* pfr = pww + mf * RSS;
