@@ -493,11 +493,14 @@ int build_feature_plan(syg_ctx* ctx, const syg_units* u, const syg_feature_param
             for (int i = 0; i < a.mel_nsweeps; ++i) a.mel_steps[i] = hv[1 + i];
         }
         a.n_mels = p->n_mels;
-        // Interval form of the projection (sygplan::MelIntervals): O(bins) per lane instead of padded tap sweeps.  Default for the
-        // transforms with several frames per warp (n_fft <= 1024); SYGB200_MEL_IV=0 keeps the sweeps, =2 also takes n_fft 2048.
+        // Interval form of the projection (sygplan::MelIntervals): O(bins) per lane instead of padded tap sweeps.  Default for every
+        // warp-kernel transform (n_fft <= 2048); SYGB200_MEL_IV=0 keeps the sweeps, =1 keeps them for n_fft 2048 only (A/B).
+        // (Until the plan learnt to carry the Nyquist weight of the last filter it was silently refused for the 44.1 kHz / 2048 / 128
+        // bank -- 7.7e-18 of rounding dust in the float table -- and "=2" measured "equal" because it never ran.  It is 10 % of the
+        // frame kernel: 5.65 -> 5.10 ms per 2 h.)
         {
             static int iv_env = -1;
-            if (iv_env < 0) { const char* e = std::getenv("SYGB200_MEL_IV"); iv_env = e ? std::atoi(e) : 1; }
+            if (iv_env < 0) { const char* e = std::getenv("SYGB200_MEL_IV"); iv_env = e ? std::atoi(e) : 2; }
             // (the frame kernel runs spectral contrast BEFORE the mel stage, so overwriting the spectrum there is safe)
             if (iv_env && fl <= ((iv_env >= 2) ? 2048 : 1024) && fl >= 128 && p->power == 2.0) {
                 std::string ki = key + ":iv", kin = key + ":ivn";

@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                         p[4 * i] = v.x; p[4 * i + 1] = v.y; p[4 * i + 2] = v.z; p[4 * i + 3] = v.w;
                     }
                 }
+                const float p_nyq = reg[ppad(M)];                       // the Nyquist bin (its word becomes the first of CF)
                 __syncwarp();                                           // every lane holds its bins before the region is overwritten
                 const float4* const wt = mw4;                           // [E/2][G] {wr, wf, wr, wf}
                 const int4* const picks = reinterpret_cast<const int4*>(mw4 + M / 2);
@@ -746,7 +747,8 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 __syncwarp();
                 for (int m = sl; m < a.n_mels; m += GS) {
                     const int4 pk4 = picks[m];                          // {r0, r1, f0, f1}
-                    const float acc = (reg[pk4.x] + reg[pk4.y]) + (reg[pk4.z] + reg[pk4.w]);
+                    float acc = (reg[pk4.x] + reg[pk4.y]) + (reg[pk4.z] + reg[pk4.w]);
+                    if (m == a.n_mels - 1) acc = __fmaf_rn(reinterpret_cast<const float*>(mw4 + M / 2 + a.n_mels + (G + 3) / 4)[0], p_nyq, acc);
                     if (fvalid) {
                         mrow[m] = acc;
                         fmx = fmaxf(fmx, acc);

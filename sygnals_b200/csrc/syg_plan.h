@@ -144,6 +144,7 @@ inline bool build_mel(double sr, int n_fft, int n_mels, double fmin, double fmax
 //                                             and fall totals in CF; both arrays use the padded spectrum layout k + 4 (k / 32), CF
 //                                             starts PSM = M + M/8 words after CR; unused picks point at word 2 PSM (kept zero)
 //                        [.., + ceil(G/4))    per lane one uint: bit b set = bin b of the lane continues its predecessor's interval
+//                        [.., + 1)            {weight of the Nyquist bin in the last filter, 0, 0, 0}
 struct MelIntervals { bool ok = false; std::vector<float> blob; int f4 = 0; };
 
 inline void build_mel_intervals(double sr, int n_fft, int n_mels, double fmin, double fmax, const MelTable& t, int E, int G,
@@ -166,8 +167,10 @@ inline void build_mel_intervals(double sr, int n_fft, int n_mels, double fmin, d
     auto rise = [&](int k) { return (iv[k] >= 0 && iv[k] <= n_mels - 1) ? iv[k] : -1; };
     auto fall = [&](int k) { return (iv[k] - 1 >= 0 && iv[k] - 1 <= n_mels - 1) ? iv[k] - 1 : -1; };
     // the model must reproduce the filter table exactly: every non-zero weight belongs to the bin's rise or fall filter
+    // Nyquist bin: outside the lanes' bins.  Only the LAST filter may weight it (fmax = sr/2: its falling edge ends there; the float
+    // table holds rounding dust such as 7.7e-18 for 44.1 kHz / 2048 / 128 mels): the kernel adds that one product explicitly.
     for (int m = 0; m < n_mels; ++m) {
-        if (t.dense[(size_t)m * B + M] != 0.0f) return;         // Nyquist bin: never weighted (fmax <= sr/2)
+        if (m != n_mels - 1 && t.dense[(size_t)m * B + M] != 0.0f) return;
         for (int k = 0; k < M; ++k)
             if (t.dense[(size_t)m * B + k] != 0.0f && m != rise(k) && m != fall(k)) return;
     }
@@ -175,8 +178,9 @@ inline void build_mel_intervals(double sr, int n_fft, int n_mels, double fmin, d
     if (M % 32) return;
     const int PSM = M + M / 8;                                  // padded length of CR (and of CF)
     auto pad = [](int k) { return k + ((k >> 5) << 2); };
-    out.f4 = f4_w + f4_p + f4_k;
+    out.f4 = f4_w + f4_p + f4_k + 1;                            // + one float4: {weight of the Nyquist bin in the last filter, 0, 0, 0}
     out.blob.assign((size_t)out.f4 * 4, 0.0f);
+    out.blob[(size_t)(f4_w + f4_p + f4_k) * 4] = t.dense[(size_t)(n_mels - 1) * B + M];
     for (int j = 0; j < G; ++j)
         for (int b = 0; b < E; ++b) {
             const int k = j * E + b;
