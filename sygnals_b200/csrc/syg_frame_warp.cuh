@@ -64,13 +64,18 @@ SYG_DEVICE SYG_INLINE int zpad(int i) { return i + (i >> LOG2E); }
 //   band(i, 0..2) = {first bin, bins, quantile count}  of sygplan::build_bands(sr, 2048, n_bands=6, fmin=200, quantile=0.02)
 //   steps(i)      = float4 steps of mel sweep i of sygplan::build_mel_slots (n_mels = 128, fmin 0, fmax sr/2, 32 filters per sweep)
 // ---------------------------------------------------------------------------------------------------------------------------
-struct SpecNone {
+// kMask != 0: the feature set and the output rows of the non-EXTRA features are compile-time constants too (SpecLayout below)
+struct SpecNoLayout {
+    static constexpr unsigned kMask = 0u;
+    static constexpr int row_rms = -1, row_crest = -1, row_peak = -1, row_centroid = -1, row_rolloff = -1;
+};
+struct SpecNone : SpecNoLayout {
     static constexpr bool kBands = false, kMel = false;
     static constexpr int nb = 0, n_sweeps = 0;
     SYG_HD static constexpr int band(int, int) { return 0; }
     SYG_HD static constexpr int steps(int) { return 0; }
 };
-struct Spec44k {                                                       // sr 44100 (BASELINE cfg4)
+struct Spec44k : SpecNoLayout {                                        // sr 44100 (BASELINE cfg4)
     static constexpr bool kBands = true, kMel = true;
     static constexpr int nb = 7, n_sweeps = 4;
     SYG_HD static constexpr int band(int i, int f) {
@@ -79,7 +84,7 @@ struct Spec44k {                                                       // sr 441
     }
     SYG_HD static constexpr int steps(int i) { constexpr int t[4] = {22, 8, 6, 6}; return t[i]; }
 };
-struct Spec22k {                                                       // sr 22050 (the reference's default sample rate; BASELINE cfg1)
+struct Spec22k : SpecNoLayout {                                        // sr 22050 (the reference's default sample rate; BASELINE cfg1)
     static constexpr bool kBands = true, kMel = true;
     static constexpr int nb = 7, n_sweeps = 4;
     SYG_HD static constexpr int band(int i, int f) {
@@ -87,6 +92,13 @@ struct Spec22k {                                                       // sr 220
         return t[i][f];
     }
     SYG_HD static constexpr int steps(int i) { constexpr int t[4] = {16, 8, 6, 4}; return t[i]; }
+};
+
+// Spec44k + the request of BASELINE cfg4 in the reference's column order: mfcc x13 | contrast x7 | centroid | rolloff | rms | crest.
+// The feature-mask branches, the "row requested?" tests and the row offsets fold into the code (launcher: spec_matches).
+struct Spec44kL : Spec44k {
+    static constexpr unsigned kMask = syg::FB_MFCC | syg::FB_CONTRAST | syg::FB_CENTROID | syg::FB_ROLLOFF | syg::FB_RMS | syg::FB_CREST;
+    static constexpr int row_rms = 22, row_crest = 23, row_peak = -1, row_centroid = 20, row_rolloff = 21;
 };
 
 template <int G>
@@ -137,6 +149,10 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     constexpr int B = M + 1;
     static_assert(R2 == G, "two-pass warp tile: the last radix equals the lanes per frame");
     constexpr bool kShflSplit = (SYG_SPLIT_SHFL != 0);                  // mirrors of the real split by SHFL (syg_device.cuh: mirror_of)
+    constexpr bool kLay = (SP::kMask != 0u);                            // feature set + rows known at compile time
+    const unsigned mask = kLay ? SP::kMask : a.mask;
+    const int row_rms = kLay ? SP::row_rms : a.row_rms, row_crest = kLay ? SP::row_crest : a.row_crest, row_peak = kLay ? SP::row_peak : a.row_peak;
+    const int row_centroid = kLay ? SP::row_centroid : a.row_centroid, row_rolloff = kLay ? SP::row_rolloff : a.row_rolloff;
     // feature stages: pass 2 produces Z/2 (halved twiddle table, element 0 entering with the pending scale 0.5) and the split runs in tangent form (split_power_h)
     constexpr bool kHalfZ = (STAGE == 0 || STAGE == 5) && (SYG_SPLIT_HALF != 0);
     SYG_DYN_SMEM(smem_raw);
@@ -191,7 +207,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             if (kHalfZ) d_twsh[i] = split_twiddle_h(__ldg(a.tws + i), 4 * i < M);
             else d_twsh[i] = __ldg((STAGE == 4 ? a.tws : a.twsh) + i);
         }
-        if ((STAGE == 0 || STAGE == 5) && (a.mask & syg::FB_MFCC)) {
+        if ((STAGE == 0 || STAGE == 5) && (mask & syg::FB_MFCC)) {
             int4* d_sl = const_cast<int4*>(t_slots);
             for (int i = tid; i < a.n_mels; i += NT) d_sl[i] = __ldg(a.mel_slots + i);
             float4* d_mw = const_cast<float4*>(t_melw);
@@ -204,7 +220,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
     constexpr bool RES = (STAGE == 5);
     const int res_P = RES ? fin_pitch(a.n_mels) : 0;
     const int res_GF8 = RES ? (a.res_units * a.T + 7) / 8 * 8 : 0;
-    float* const res_tile = reinterpret_cast<float*>(tb + (RES ? WT::table_bytes(a.n_mels, (a.mask & syg::FB_MFCC) ? a.mel_pw_f4 : 0) : 0));
+    float* const res_tile = reinterpret_cast<float*>(tb + (RES ? WT::table_bytes(a.n_mels, (mask & syg::FB_MFCC) ? a.mel_pw_f4 : 0) : 0));
     float* const res_ref = res_tile + (size_t)res_GF8 * res_P;
     long long* const res_out = reinterpret_cast<long long*>(res_ref + res_GF8);          // res_GF8 is even: 8-byte aligned
     unsigned* const res_umax = reinterpret_cast<unsigned*>(res_out + res_GF8);
@@ -485,18 +501,18 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             continue;
         }
         // ---------------- time-domain features (unwindowed, zero-padded frame) ----------------
-        if (a.mask & syg::FB_TIME_ANY) {
+        if (mask & syg::FB_TIME_ANY) {
             const float tsq = lanes_sum<G>(sq2.x + sq2.y);
             const float tpk = lanes_max<G>(pk);
             if (j == 0 && valid) {
                 const float rms = sqrt_approx(tsq * (1.0f / (float)TL::NFFT));     // MUFU.SQRT (1 ulp) instead of the IEEE sequence; bar: rel 1e-5
-                if (a.row_rms >= 0) orow[(long long)a.row_rms * a.T] = rms;
+                if (row_rms >= 0) orow[(long long)row_rms * a.T] = rms;
                 // eps(float64) = 2^-52 is a float too: the reference's `rms < eps` on the widened value is this float comparison
-                if (a.row_crest >= 0) orow[(long long)a.row_crest * a.T] = (rms < 2.220446049250313e-16f) ? 0.0f : __fdividef(tpk, rms);
-                if (a.row_peak >= 0) orow[(long long)a.row_peak * a.T] = tpk;
+                if (row_crest >= 0) orow[(long long)row_crest * a.T] = (rms < 2.220446049250313e-16f) ? 0.0f : __fdividef(tpk, rms);
+                if (row_peak >= 0) orow[(long long)row_peak * a.T] = tpk;
             }
             if (EXTRA) {
-                if (a.mask & (syg::FB_STD_AMP | syg::FB_MEAN_AMP)) {
+                if (mask & (syg::FB_STD_AMP | syg::FB_MEAN_AMP)) {
                     const double tsum = lanes_sum<G>(s_sum), tabs = lanes_sum<G>(s_abs), tsqd = lanes_sum<G>(s_sqd);
                     if (j == 0 && valid) {
                         const double n = (double)TL::NFFT;
@@ -513,7 +529,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         }
 
         // ---------------- per-frame spectral statistics (lane j owns bins [j*E, j*E+E), last lane also bin M) ----------------
-        if (a.mask & syg::FB_SPECSTATS) {
+        if (mask & syg::FB_SPECSTATS) {
             const int k0 = j * E;
             float p[E];
             {
@@ -539,7 +555,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 if (EXTRA) {
                     SYG_UNROLL
                     for (int h = 0; h < 2; ++h) {
-                        if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p[i + h]) + 2.220446049250313e-16f);
+                        if (mask & syg::FB_FLATNESS) slog += logf(sqrtf(p[i + h]) + 2.220446049250313e-16f);
                         if (p[i + h] > vmax) { vmax = p[i + h]; imax = k0 + i + h; }
                     }
                 }
@@ -554,7 +570,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                 lsm += mg;
                 lskm = __fmaf_rn(mg, (float)M, lskm);
                 if (EXTRA) {
-                    if (a.mask & syg::FB_FLATNESS) slog += logf(sqrtf(p_ny) + 2.220446049250313e-16f);
+                    if (mask & syg::FB_FLATNESS) slog += logf(sqrtf(p_ny) + 2.220446049250313e-16f);
                     if (p_ny > vmax) { vmax = p_ny; imax = M; }
                 }
             }
@@ -567,13 +583,13 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
             double centroid_hz = 0.0;
             if constexpr (EXTRA) {                                       // spectral_bandwidth needs the float64 centroid
                 if ((double)tm >= kEps64) centroid_hz = a.bin_hz * ((double)tkm / (double)tm);
-                if (a.row_centroid >= 0 && j == 0 && valid) orow[(long long)a.row_centroid * a.T] = (float)centroid_hz;
+                if (row_centroid >= 0 && j == 0 && valid) orow[(long long)row_centroid * a.T] = (float)centroid_hz;
             } else {
                 // the sums are FP32 already; one FP32 division (2^-23 relative against a 1e-5 parity bar) instead of a float64 one
                 const float c = (tm >= 2.220446049250313e-16f) ? (float)a.bin_hz * __fdividef(tkm, tm) : 0.0f;
-                if (a.row_centroid >= 0 && j == 0 && valid) orow[(long long)a.row_centroid * a.T] = c;
+                if (row_centroid >= 0 && j == 0 && valid) orow[(long long)row_centroid * a.T] = c;
             }
-            if (a.row_rolloff >= 0) {
+            if (row_rolloff >= 0) {
                 // first bin whose cumulative power reaches roll_percent * total (frequency_domain.py:334-346)
                 const double thr = a.roll_percent * total_p;
                 const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << (f * G));
@@ -612,7 +628,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
                     if (total_p < kEps64) bin = M;                                      // silent frame -> freqs[-1]
                     else if (found) bin = kL + posw;
                     else bin = (L == G - 1) ? M : kL + E - 1;                           // only the lane's last element is left
-                    orow[(long long)a.row_rolloff * a.T] = (float)(a.bin_hz * (double)bin);
+                    orow[(long long)row_rolloff * a.T] = (float)(a.bin_hz * (double)bin);
                 }
             }
             if (EXTRA) {
@@ -653,7 +669,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         }
 
         // ---------------- spectral contrast: per band mean of the n largest / n smallest magnitudes ----------------
-        if (a.mask & syg::FB_CONTRAST) {
+        if (mask & syg::FB_CONTRAST) {
             for (int ff = 0; ff < FW; ++ff) {
                 const long long gff = tf0 + ff;
                 if (!kSkipInvalid && gff >= frame_end) break;
@@ -690,7 +706,7 @@ __global__ void __launch_bounds__(NT, MINB) frame_warp_kernel(const syg::FrameAr
         // ---------------- mel energies: one filter per lane; the warp sweeps GS = 32 / FW filters of each of its frames at once ----------------
         // (Loading a tap vector once for all FW frames of the task -- 32 filters per sweep, frames in an inner loop -- was measured:
         // fewer shared-memory wavefronts but 7 instead of 4 instructions per step and idle lanes in the last sweep; cfg3 +10 % time.)
-        if (a.mask & syg::FB_MFCC) {
+        if (mask & syg::FB_MFCC) {
             constexpr int GS = 32 / FW;
             const int mf = lane / GS, sl = lane % GS;                   // frame of the warp task, slot within the sweep group
             const long long gmf = tf0 + mf;

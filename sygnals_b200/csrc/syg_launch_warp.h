@@ -15,6 +15,7 @@ namespace syglaunch {
 // plan-specialised instantiations of the n_fft 2048 feature kernel (own translation units: syg_launch_warp_spec*.cu)
 int frame_warp_spec44k(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 int frame_warp_spec22k(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
+int frame_warp_spec44kl(const syg::FrameArgs& a, int sm_count, cudaStream_t st, std::string& err);
 
 // STAGE 0: features; 3: STFT output through a CTA tile; 4: STFT magnitude / power through warp-private tiles (see syg_frame_warp.cuh)
 template <class TL, bool EXTRA, int NT, int MINB, int STAGE, class SP = sygdev::SpecNone>
@@ -47,6 +48,8 @@ static int frame_warp_t(const syg::FrameArgs& a, int sm_count, cudaStream_t st, 
 template <class SP>
 static bool spec_matches(const syg::FrameArgs& a) {
     if (!(a.mask & (syg::FB_MFCC | syg::FB_CONTRAST))) return false;
+    if (SP::kMask && (a.mask != SP::kMask || a.row_rms != SP::row_rms || a.row_crest != SP::row_crest || a.row_peak != SP::row_peak ||
+                      a.row_centroid != SP::row_centroid || a.row_rolloff != SP::row_rolloff)) return false;
     if (a.mask & syg::FB_CONTRAST) {
         if (!SP::kBands || a.nb != SP::nb) return false;
         for (int i = 0; i < SP::nb; ++i)
@@ -85,6 +88,9 @@ static int frame_warp_dispatch(int n_fft, const syg::FrameArgs& a, int sm_count,
             if constexpr (STAGE == 0 && !EXTRA) {
                 static int nospec = -1;                               // SYGB200_NO_SPEC=1: always the generic loops (A/B measurements)
                 if (nospec < 0) { const char* e = std::getenv("SYGB200_NO_SPEC"); nospec = e ? std::atoi(e) : 0; }
+                static int nolay = -1;                                // SYGB200_NO_SPECL=1: skip the layout-specialised instantiation (A/B)
+                if (nolay < 0) { const char* e = std::getenv("SYGB200_NO_SPECL"); nolay = e ? std::atoi(e) : 0; }
+                if (!nospec && !nolay && spec_matches<Spec44kL>(a)) return frame_warp_spec44kl(a, sm_count, st, err);
                 if (!nospec && spec_matches<Spec44k>(a)) return frame_warp_spec44k(a, sm_count, st, err);
                 if (!nospec && spec_matches<Spec22k>(a)) return frame_warp_spec22k(a, sm_count, st, err);
             }
