@@ -672,7 +672,10 @@ struct Sel4 {                        // one lane's view of a band: four largest 
 // instead of 14 for element-wise insertion).
 template <bool ST>
 SYG_DEVICE SYG_INLINE Sel4 track4(const float* __restrict__ q, int mine, int count) {
-    constexpr int UQ = ST ? 8 : 1, US = ST ? 4 : 1;             // static band layout: trip counts are constants -> straight-line code
+#ifndef SYG_TRACK_UNROLL
+#define SYG_TRACK_UNROLL 8
+#endif
+    constexpr int UQ = ST ? SYG_TRACK_UNROLL : 1, US = ST ? 4 : 1;             // static band layout: trip counts are constants -> straight-line code
     Sel4 t;
     t.a0 = t.a1 = t.a2 = t.a3 = 0u;
     t.b0 = t.b1 = t.b2 = t.b3 = 0xffffffffu;
