@@ -129,20 +129,17 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
             if (a.stats && valid) {
                 const int lim = (s == a.nseg - 1) ? a.nperseg : a.step;
                 float2 sq = make_float2(0.0f, 0.0f);
-                float pk2 = 0.0f;
                 SYG_UNROLL
                 for (int r = 0; r < E; ++r) {
                     const int c2 = 2 * (j + r * G);
                     if (c2 + 1 < lim) {
                         sq = __ffma2_rn(z[r], z[r], sq);
-                        pk = fmaxf(pk, fabsf(z[r].x));
-                        pk2 = fmaxf(pk2, fabsf(z[r].y));
+                        pk = fmaxf(fmaxf(pk, fabsf(z[r].x)), fabsf(z[r].y));   // one FMNMX3
                     } else if (c2 < lim) {
                         sq.x = __fmaf_rn(z[r].x, z[r].x, sq.x);
                         pk = fmaxf(pk, fabsf(z[r].x));
                     }
                 }
-                pk = fmaxf(pk, pk2);
                 sqd += (double)(sq.x + sq.y);                          // float32 partial sums of <= 2 E terms, float64 across
             }
             float mean = 0.0f;
@@ -150,10 +147,11 @@ __global__ void __launch_bounds__(NT, MINB) welch_warp_kernel(const syg::WelchAr
                 const double tot = lanes_sum<G>((double)((sm01.x + sm01.y) + (sm23.x + sm23.y)));
                 mean = (float)(tot * (double)inv_n);
             }
+            const float2 nmean2 = make_float2(-mean, -mean);
             SYG_UNROLL
             for (int r = 0; r < E; ++r) {
                 const float2 w = TBLW ? w2[j + r * G] : __ldg(w2 + j + r * G);   // zero beyond nperseg: padding samples vanish
-                z[r] = make_float2((z[r].x - mean) * w.x, (z[r].y - mean) * w.y);
+                z[r] = __fmul2_rn(__fadd2_rn(z[r], nmean2), w);         // (z - mean) * w, both halves at once
             }
             // ---------------- FFT (as in frame_warp_kernel) ----------------
             dft_dif_p<E, 1>(z);
