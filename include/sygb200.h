@@ -223,6 +223,9 @@ int syg_spectral_contrast_from_mag_f32(syg_ctx* ctx, const float* S_dev, int32_t
 int syg_debug_last_stft_path(void);
 /* 1 when the last feature launch kept its (short) units on chip: mel tile + dB + DCT inside the frame kernel, no finalize launch */
 int syg_debug_last_features_resident(void);
+/* mel projection of the last feature launch with MFCCs: 1 interval form (running sums per mel interval + picks), 0 padded tap sweeps
+ * (the form is refused for banks its planner cannot represent; tests pin it for the BASELINE banks so that a refusal is not silent) */
+int syg_debug_last_mel_form(void);
 /* unit groups a launch needs before the resident kernel is chosen (default -1: four per SM); tests set 1 to drive it with few units */
 void syg_debug_set_resident_min_groups(int n);
 int syg_debug_window(int32_t window, int32_t win_length, int32_t n_fft, float* out);

@@ -114,6 +114,7 @@ class Library:
             "syg_spectral_contrast_from_mag_f32": (C.c_int, [vp, vp, i32, i64, f64, i32, f64, f64, vp, vp]),
             "syg_debug_last_stft_path": (C.c_int, []),
             "syg_debug_last_features_resident": (C.c_int, []),
+            "syg_debug_last_mel_form": (C.c_int, []),
             "syg_debug_set_resident_min_groups": (None, [C.c_int]),
             "syg_debug_window": (C.c_int, [i32, i32, i32, vp]),
             "syg_debug_mel_basis": (C.c_int, [i32, i32, i32, f64, f64, vp]),

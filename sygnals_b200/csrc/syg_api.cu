@@ -304,6 +304,7 @@ int warp_fw(int n_fft) {
 }
 
 int g_resident_min_groups = -1;     // unit groups a launch needs before the resident kernel is chosen (-1: 4 per SM); tests lower it
+int g_last_mel_form = 0;            // 1: the last feature launch with MFCCs used the interval-form mel projection
 int g_last_features_resident = 0;   // 1: the last feature launch kept its units on chip (frame_warp_kernel STAGE 5)
 int g_last_stft_path = 0;   // 5 mixed-radix kernel (lengths that are not powers of two), 1 ring (TMA-staged), 2 warp kernel (register-staged), 3 CTA-cooperative kernels, 4 sub-FFT kernel (n_fft 4096 / 8192): last STFT launch
 
@@ -602,6 +603,7 @@ int run_features_chunk(syg_ctx* ctx, const FeaturePlan& pl, const float* y, cons
         }
     }
     g_last_features_resident = a.res_units > 0 ? 1 : 0;
+    if (a.mask & syg::FB_MFCC) g_last_mel_form = a.mel_iv ? 1 : 0;
     const bool need_fin = (a.mask & (syg::FB_MFCC | syg::FB_CONTRAST)) != 0 && a.res_units == 0;
     if (need_fin) CK(cudaMemsetAsync(a.unit_max, 0, (size_t)g.n_units * 4 * sizeof(unsigned), st));
     int rc = SYG_OK;
@@ -1355,6 +1357,7 @@ int syg_spectral_contrast_from_mag_f32(syg_ctx* ctx, const float* S_dev, int32_t
 
 int syg_debug_last_stft_path(void) { return g_last_stft_path; }
 int syg_debug_last_features_resident(void) { return g_last_features_resident; }
+int syg_debug_last_mel_form(void) { return g_last_mel_form; }
 void syg_debug_set_resident_min_groups(int n) { g_resident_min_groups = n; }
 
 int syg_debug_window(int32_t window, int32_t win_length, int32_t n_fft, float* out) {
