@@ -46,3 +46,23 @@ def test_nyquist_weight_of_the_last_filter_is_applied(eng):
     assert eng.lib.dll.syg_debug_last_mel_form() == 1
     names, ref = oracle_rows(y[0], sr, ["mfcc"], n_fft, hop, fp)
     check_rows(names, out[0], ref)
+
+
+def test_layout_specialised_kernel_equals_the_plan_specialised_one(eng):
+    """BASELINE cfg4's request in the reference's column order runs on Spec44kL (feature set + rows as compile-time constants); the
+    same features in another order miss its layout and run on Spec44k.  Same arithmetic: the rows must agree bit for bit."""
+    sr, n_fft, hop, L = 44100, 2048, 512, 9000
+    y = np.stack([synth.long_signal(L, sr, seed=31 + c).astype(np.float32) for c in range(2)])
+    order_l = ["mfcc", "spectral_contrast", "spectral_centroid", "spectral_rolloff", "rms_energy", "crest_factor"]
+    order_p = ["rms_energy", "mfcc", "crest_factor", "spectral_contrast", "spectral_rolloff", "spectral_centroid"]
+    from sygnals_b200.batch import feature_row_names
+    u = eng.units_clips(y.shape[0], y.shape[1])
+    out_l = eng.features_host(y.ravel(), u, _ffi.make_params(eng.lib, sr, order_l, n_fft, hop))
+    out_p = eng.features_host(y.ravel(), u, _ffi.make_params(eng.lib, sr, order_p, n_fft, hop))
+    names_l, names_p = feature_row_names(order_l, None), feature_row_names(order_p, None)
+    assert sorted(names_l) == sorted(names_p) and len(names_l) == 24
+    for i, n in enumerate(names_l):
+        assert np.array_equal(out_l[:, i], out_p[:, names_p.index(n)]), n
+    for c in range(y.shape[0]):
+        names, ref = oracle_rows(y[c], sr, order_l, n_fft, hop)
+        check_rows(names, out_l[c], ref, bin_hz=sr / n_fft, nyq=sr / 2)
