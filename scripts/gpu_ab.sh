@@ -6,7 +6,7 @@ line() { python bench.py --hours ${HOURS:-2} --steps 5 --warmup 3 --no-e2e --no-
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):
-        d=json.loads(ln); r=d['roofline']; print('$1 ms/step %.3f frame %.3f finalize %.3f' % (d['ms_per_step'], r['kernel_ms_per_step'], r['finalize_ms_per_step']))
+        d=json.loads(ln); r=d['roofline']; print('$1 ms/step %.3f frame %.3f finalize %.3f aggregate %.3f' % (d['ms_per_step'], r['kernel_ms_per_step'], r['finalize_ms_per_step'], r.get('aggregate_ms_per_step', 0.0)))
 "; }
 for i in $(seq ${REPS:-3}); do
   cp /tmp/lib_main.so sygnals_b200/libsygb200.so; line main

@@ -64,9 +64,16 @@ __global__ void __launch_bounds__(kThreads) aggregate_kernel(const AggArgs a) {
             int n = 0;
             double sum = 0.0;
             float mn = __uint_as_float(0x7f800000u), mx = __uint_as_float(0xff800000u);
-            for (int i = lane; i < len; i += 32) {
-                const float v = x[i];
-                if (v == v) { ++n; sum += (double)v; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+            // eight loads in flight per lane before the first use (a warp walks ~90 items one after the other: the dependent
+            // load -> FP64 add chain of the plain loop left the kernel latency bound); same elements in the same order per lane
+            const float fnan = __uint_as_float(0x7fc00000u);
+            for (int i0 = lane; i0 < len; i0 += 256) {
+                float v[8];
+                SYG_UNROLL
+                for (int k = 0; k < 8; ++k) v[k] = (i0 + 32 * k < len) ? x[i0 + 32 * k] : fnan;
+                SYG_UNROLL
+                for (int k = 0; k < 8; ++k)
+                    if (v[k] == v[k]) { ++n; sum += (double)v[k]; mn = fminf(mn, v[k]); mx = fmaxf(mx, v[k]); }
             }
             n = __reduce_add_sync(kFull, n);
             if (n > 0) {                                            // formatters.py:31-36: all-NaN -> NaN
@@ -76,9 +83,13 @@ __global__ void __launch_bounds__(kThreads) aggregate_kernel(const AggArgs a) {
                     res = mean;
                     if (kind == 1) {                                // np.std: population (ddof = 0), two passes
                         double ss = 0.0;
-                        for (int i = lane; i < len; i += 32) {
-                            const float v = x[i];
-                            if (v == v) { const double d = (double)v - mean; ss += d * d; }
+                        for (int i0 = lane; i0 < len; i0 += 256) {
+                            float v[8];
+                            SYG_UNROLL
+                            for (int k = 0; k < 8; ++k) v[k] = (i0 + 32 * k < len) ? x[i0 + 32 * k] : fnan;
+                            SYG_UNROLL
+                            for (int k = 0; k < 8; ++k)
+                                if (v[k] == v[k]) { const double d = (double)v[k] - mean; ss += d * d; }
                         }
                         res = sqrt(warp_sum_d(ss) / (double)n);
                     }
