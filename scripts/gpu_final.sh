@@ -7,7 +7,7 @@ python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/${TAG}_tests.log; t
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cut -c1-200 gpurun_out/${TAG}_bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; cut -c1-200 gpurun_out/${TAG}_bench_reference.json
-for wl in cfg2 cfg3 cfg5; do python bench.py --workload $wl --no-cpu > gpurun_out/${TAG}_bench_${wl}.json 2>> gpurun_out/${TAG}_bench.err; cut -c1-160 gpurun_out/${TAG}_bench_${wl}.json; done
+for wl in cfg1 cfg2 cfg3 cfg5; do python bench.py --workload $wl --no-cpu > gpurun_out/${TAG}_bench_${wl}.json 2>> gpurun_out/${TAG}_bench.err; cut -c1-160 gpurun_out/${TAG}_bench_${wl}.json; done
 CMD="python bench.py --steps 2 --warmup 3 --hours 1 --no-e2e --no-cpu --no-weak"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"frame_warp|finalize|aggregate|pcm|time_extra" -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu.log 2>&1
 CMD="python bench.py --hours 0.5 --steps 1 --warmup 1 --no-e2e --no-cpu --no-weak"

@@ -3,7 +3,7 @@
 T=${1:?tag}
 G=gpurun_out; P=profiles
 FR=311400   # frames of one launch of `bench.py --hours 0.5` (1800 segments x 173 frames)
-for f in bench bench_reference bench_cfg2 bench_cfg3 bench_cfg5; do [ -s $G/${T}_$f.json ] && grep '^{' $G/${T}_$f.json > $P/${T}_$f.json; done
+for f in bench bench_reference bench_cfg1 bench_cfg2 bench_cfg3 bench_cfg5; do [ -s $G/${T}_$f.json ] && grep '^{' $G/${T}_$f.json > $P/${T}_$f.json; done
 [ -s $G/${T}_launches.csv ] && cp $G/${T}_launches.csv $P/${T}_launches.csv
 [ -s $G/${T}_tests.log ] && cp $G/${T}_tests.log $P/${T}_gpu_tests_tail.txt
 [ -s $G/${T}_smoke.log ] && cp $G/${T}_smoke.log $P/${T}_smoke.log
